@@ -1,0 +1,727 @@
+// C ABI of libcocos_b200.so (declared in include/cocos_b200.h).
+// Host-side glue only: argument checks, launch-constant preparation in double
+// precision, launch geometry, NCCL (loaded lazily with dlopen), error strings.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "kernels.h"
+
+using namespace cb;
+
+// ---------------------------------------------------------------- errors
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CB_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(CB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                      \
+    } while (0)
+
+#define CB_REQUIRE(cond, ...)                                \
+    do {                                                     \
+        if (!(cond)) return fail(CB_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// ---------------------------------------------------------------- context
+
+struct cb_ctx {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    ReduceWorkspace ws{};
+    unsigned long long *d_inside = nullptr;
+    double *h_result = nullptr;              // pinned, kMaxAcc doubles + one u64
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    void *scratch = nullptr;                 // grow-only staging buffer for the *_host entry points
+    size_t scratch_bytes = 0;
+    int threads = 0, blocks_per_sm = 0, ppt = 0;   // 0 = default
+    std::map<std::tuple<int, int, int, int>, std::pair<int, int>> occ_cache;   // (is64, ppt, multi, threads) -> (bps, regs)
+};
+
+struct cb_comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 0, rank = 0;
+};
+
+extern "C" CB_API const char *cb_last_error(void) { return g_err; }
+extern "C" CB_API const char *cb_version(void) { return "cocos_b200 0.1 (sm_100a)"; }
+
+extern "C" CB_API int cb_device_count(int *n) {
+    CB_REQUIRE(n != nullptr, "n is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(CB_ERR_CUDA, "cudaGetDeviceCount failed: %s (no CPU fallback exists)", cudaGetErrorString(e));
+    }
+    *n = c;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_device_name(int dev, char *buf, size_t buflen) {
+    CB_REQUIRE(buf != nullptr && buflen > 0, "bad buffer");
+    cudaDeviceProp p;
+    CB_CUDA(cudaGetDeviceProperties(&p, dev));
+    snprintf(buf, buflen, "%s", p.name);
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_device_attributes(int dev, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+    cudaDeviceProp p;
+    CB_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_ctx_create(int dev, void *stream_or_null, cb_ctx **out) {
+    CB_REQUIRE(out != nullptr, "out is NULL");
+    int n = 0;
+    int rc = cb_device_count(&n);
+    if (rc != CB_OK) return rc;
+    CB_REQUIRE(dev >= 0 && dev < n, "device %d out of range (%d devices)", dev, n);
+    CB_CUDA(cudaSetDevice(dev));
+    cb_ctx *c = new cb_ctx();
+    c->dev = dev;
+    if (stream_or_null != nullptr) {
+        c->stream = (cudaStream_t)stream_or_null;
+    } else {
+        CB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    CB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CB_CUDA(cudaMalloc(&c->ws.partials, sizeof(double) * (size_t)kMaxGridBlocks * kMaxAcc));
+    CB_CUDA(cudaMalloc(&c->ws.ticket, sizeof(unsigned int)));
+    CB_CUDA(cudaMalloc(&c->ws.result, sizeof(double) * kMaxAcc));
+    CB_CUDA(cudaMalloc(&c->d_inside, sizeof(unsigned long long)));
+    CB_CUDA(cudaMemset(c->ws.ticket, 0, sizeof(unsigned int)));
+    CB_CUDA(cudaMemset(c->ws.result, 0, sizeof(double) * kMaxAcc));
+    CB_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * (kMaxAcc + 1)));
+    CB_CUDA(cudaEventCreate(&c->ev_start));
+    CB_CUDA(cudaEventCreate(&c->ev_stop));
+    *out = c;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_ctx_destroy(cb_ctx *c) {
+    if (c == nullptr) return CB_OK;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->ws.partials);
+    cudaFree(c->ws.ticket);
+    cudaFree(c->ws.result);
+    cudaFree(c->d_inside);
+    cudaFree(c->scratch);
+    cudaFreeHost(c->h_result);
+    cudaEventDestroy(c->ev_start);
+    cudaEventDestroy(c->ev_stop);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CB_OK;
+}
+
+#define CB_CTX(c)                                   \
+    CB_REQUIRE((c) != nullptr, "context is NULL"); \
+    CB_CUDA(cudaSetDevice((c)->dev))
+
+extern "C" CB_API int cb_ctx_sync(cb_ctx *c) {
+    CB_CTX(c);
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_ctx_device(cb_ctx *c, int *dev) {
+    CB_REQUIRE(c != nullptr && dev != nullptr, "NULL argument");
+    *dev = c->dev;
+    return CB_OK;
+}
+
+extern "C" CB_API void *cb_ctx_stream(cb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" CB_API int cb_timer_start(cb_ctx *c) {
+    CB_CTX(c);
+    CB_CUDA(cudaEventRecord(c->ev_start, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_timer_stop(cb_ctx *c, float *elapsed_ms) {
+    CB_CTX(c);
+    CB_REQUIRE(elapsed_ms != nullptr, "elapsed_ms is NULL");
+    CB_CUDA(cudaEventRecord(c->ev_stop, c->stream));
+    CB_CUDA(cudaEventSynchronize(c->ev_stop));
+    CB_CUDA(cudaEventElapsedTime(elapsed_ms, c->ev_start, c->ev_stop));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_ctx_set_launch(cb_ctx *c, int threads, int blocks_per_sm, int pairs_per_thread) {
+    CB_REQUIRE(c != nullptr, "context is NULL");
+    CB_REQUIRE(threads == 0 || (threads >= 32 && threads <= 256 && threads % 32 == 0), "threads must be 0 or a multiple of 32 in [32,256]");
+    CB_REQUIRE(blocks_per_sm >= 0 && blocks_per_sm <= 32, "blocks_per_sm must be in [0,32]");
+    CB_REQUIRE(pairs_per_thread == 0 || pairs_per_thread == 1 || pairs_per_thread == 2 || pairs_per_thread == 4,
+               "pairs_per_thread must be 0, 1, 2 or 4");
+    c->threads = threads;
+    c->blocks_per_sm = blocks_per_sm;
+    c->ppt = pairs_per_thread;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_malloc(cb_ctx *c, size_t bytes, void **d_ptr) {
+    CB_CTX(c);
+    CB_REQUIRE(d_ptr != nullptr, "d_ptr is NULL");
+    CB_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_free(cb_ctx *c, void *d_ptr) {
+    CB_CTX(c);
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    CB_CUDA(cudaFree(d_ptr));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_memcpy_h2d(cb_ctx *c, void *d_dst, const void *h_src, size_t bytes) {
+    CB_CTX(c);
+    CB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_memcpy_d2h(cb_ctx *c, void *h_dst, const void *d_src, size_t bytes) {
+    CB_CTX(c);
+    CB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    return CB_OK;
+}
+
+static int ensure_scratch(cb_ctx *c, size_t bytes) {
+    if (c->scratch_bytes >= bytes) return CB_OK;
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->scratch) CB_CUDA(cudaFree(c->scratch));
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+    CB_CUDA(cudaMalloc(&c->scratch, bytes));
+    c->scratch_bytes = bytes;
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------- NCCL (lazy)
+
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+void load_nccl() {
+    // prefer a libnccl already mapped into the process (torch's bundled copy), else the system one
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle)
+        for (const char *nm : names) {
+            g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.handle) break;
+        }
+    if (!g_nccl.handle) return;
+#define CB_SYM(field, name) \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, name); \
+    if (!g_nccl.field) return;
+    CB_SYM(GetUniqueId, "ncclGetUniqueId")
+    CB_SYM(CommInitRank, "ncclCommInitRank")
+    CB_SYM(CommInitAll, "ncclCommInitAll")
+    CB_SYM(CommDestroy, "ncclCommDestroy")
+    CB_SYM(AllReduce, "ncclAllReduce")
+    CB_SYM(GroupStart, "ncclGroupStart")
+    CB_SYM(GroupEnd, "ncclGroupEnd")
+    CB_SYM(GetErrorString, "ncclGetErrorString")
+#undef CB_SYM
+    g_nccl.ok = true;
+}
+
+int need_nccl() {
+    std::call_once(g_nccl_once, load_nccl);
+    if (!g_nccl.ok) return fail(CB_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbol");
+    return CB_OK;
+}
+}  // namespace
+
+#define CB_NCCL(expr)                                                                                     \
+    do {                                                                                                  \
+        ncclResult_t r__ = (expr);                                                                        \
+        if (r__ != ncclSuccess)                                                                           \
+            return fail(CB_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(r__), __FILE__, \
+                        __LINE__);                                                                        \
+    } while (0)
+
+static_assert(sizeof(ncclUniqueId) == CB_UNIQUE_ID_BYTES, "unique id size");
+
+extern "C" CB_API int cb_comm_unique_id(void *h_id) {
+    CB_REQUIRE(h_id != nullptr, "h_id is NULL");
+    int rc = need_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    CB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(h_id, &id, sizeof id);
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_comm_init_rank(cb_ctx *c, int nranks, int rank, const void *h_id, cb_comm **out) {
+    CB_CTX(c);
+    CB_REQUIRE(out != nullptr && h_id != nullptr, "NULL argument");
+    CB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d of %d", rank, nranks);
+    int rc = need_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, h_id, sizeof id);
+    cb_comm *m = new cb_comm();
+    m->nranks = nranks;
+    m->rank = rank;
+    ncclResult_t r = g_nccl.CommInitRank(&m->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        delete m;
+        return fail(CB_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+    }
+    *out = m;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_comm_init_all(int n, cb_ctx *const *ctxs, cb_comm **out) {
+    CB_REQUIRE(n >= 1 && ctxs != nullptr && out != nullptr, "bad arguments");
+    int rc = need_nccl();
+    if (rc) return rc;
+    int devs[64];
+    CB_REQUIRE(n <= 64, "too many devices");
+    for (int i = 0; i < n; ++i) {
+        CB_REQUIRE(ctxs[i] != nullptr, "context %d is NULL", i);
+        devs[i] = ctxs[i]->dev;
+    }
+    ncclComm_t comms[64];
+    CB_NCCL(g_nccl.CommInitAll(comms, n, devs));
+    for (int i = 0; i < n; ++i) {
+        out[i] = new cb_comm();
+        out[i]->comm = comms[i];
+        out[i]->nranks = n;
+        out[i]->rank = i;
+    }
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_comm_destroy(cb_comm *m) {
+    if (m == nullptr) return CB_OK;
+    if (g_nccl.ok && m->comm) g_nccl.CommDestroy(m->comm);
+    delete m;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_allreduce_sum_f64(cb_ctx *c, cb_comm *m, double *d_buf, size_t count) {
+    CB_CTX(c);
+    CB_REQUIRE(m != nullptr && d_buf != nullptr, "NULL argument");
+    CB_NCCL(g_nccl.AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, m->comm, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_group_start(void) {
+    int rc = need_nccl();
+    if (rc) return rc;
+    CB_NCCL(g_nccl.GroupStart());
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_group_end(void) {
+    int rc = need_nccl();
+    if (rc) return rc;
+    CB_NCCL(g_nccl.GroupEnd());
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------- random arrays
+
+static int check_out(cb_ctx *c, const void *d_out, uint64_t n) {
+    CB_CTX(c);
+    CB_REQUIRE(d_out != nullptr || n == 0, "d_out is NULL");
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_philox_words(cb_ctx *c, uint32_t *d_out, uint64_t n_blocks, uint64_t first_index, uint32_t block,
+                               uint64_t seed, uint32_t subsequence) {
+    int rc = check_out(c, d_out, n_blocks);
+    if (rc) return rc;
+    CB_CUDA(launch_philox_words(d_out, n_blocks, first_index, block, philox_keys_from_seed(seed), subsequence,
+                                c->stream));
+    return CB_OK;
+}
+
+#define CB_FILL(name, real, normal)                                                                        \
+    extern "C" CB_API int name(cb_ctx *c, real *d_out, uint64_t n, uint64_t seed, uint32_t subsequence) {        \
+        int rc = check_out(c, d_out, n);                                                                   \
+        if (rc) return rc;                                                                                 \
+        CB_CUDA((launch_random_fill<real, normal>(d_out, n, philox_keys_from_seed(seed), subsequence,      \
+                                                  c->stream)));                                            \
+        return CB_OK;                                                                                      \
+    }
+CB_FILL(cb_rand_f32, float, false)
+CB_FILL(cb_rand_f64, double, false)
+CB_FILL(cb_randn_f32, float, true)
+CB_FILL(cb_randn_f64, double, true)
+
+// mirrors verify_shape_and_antithetic_dimension (cocos/numerics/random.py:103-120)
+static int split_shape(const uint64_t *dims, int ndim, int axis, uint64_t *outer, uint64_t *d, uint64_t *inner) {
+    CB_REQUIRE(dims != nullptr, "dims is NULL");
+    CB_REQUIRE(ndim <= 4, "arrays with more than 4 axes are not supported");
+    CB_REQUIRE(ndim >= 1, "array must have at least one axis");
+    CB_REQUIRE(axis >= 0 && axis <= ndim - 1, "antithetic dimension must be None or between 0 and %d", ndim);
+    *outer = 1;
+    *inner = 1;
+    for (int i = 0; i < axis; ++i) *outer *= dims[i];
+    for (int i = axis + 1; i < ndim; ++i) *inner *= dims[i];
+    *d = dims[axis];
+    return CB_OK;
+}
+
+#define CB_ANTI(name, real, normal)                                                                           \
+    extern "C" CB_API int name(cb_ctx *c, real *d_out, const uint64_t *dims, int ndim, int axis, uint64_t seed,      \
+                        uint32_t subsequence) {                                                               \
+        uint64_t outer, d, inner;                                                                             \
+        int rc = split_shape(dims, ndim, axis, &outer, &d, &inner);                                           \
+        if (rc) return rc;                                                                                    \
+        rc = check_out(c, d_out, outer * d * inner);                                                          \
+        if (rc) return rc;                                                                                    \
+        CB_CUDA((launch_random_antithetic<real, normal>(d_out, outer, d, inner, philox_keys_from_seed(seed),  \
+                                                        subsequence, c->stream)));                            \
+        return CB_OK;                                                                                         \
+    }
+CB_ANTI(cb_randn_antithetic_f32, float, true)
+CB_ANTI(cb_randn_antithetic_f64, double, true)
+CB_ANTI(cb_rand_antithetic_f32, float, false)
+CB_ANTI(cb_rand_antithetic_f64, double, false)
+
+// ---------------------------------------------------------------- Heston: parity kernels
+
+static int check_heston(const cb_heston_params *p, uint64_t R, uint32_t N) {
+    CB_REQUIRE(p != nullptr, "params is NULL");
+    CB_REQUIRE(R >= 1, "R must be >= 1");
+    CB_REQUIRE(N >= 2, "N must be >= 2 (N-1 Euler steps)");
+    CB_REQUIRE(p->rho >= -1.0 && p->rho <= 1.0, "rho must be in [-1,1]");
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_heston_terminal_injected_f32(cb_ctx *c, const float *d_Z, const cb_heston_params *p, uint64_t R,
+                                               uint32_t N, float *d_x, float *d_v) {
+    CB_CTX(c);
+    int rc = check_heston(p, R, N);
+    if (rc) return rc;
+    CB_REQUIRE(d_Z && d_x && d_v, "NULL device pointer");
+    const double dt = p->T / (double)(N - 1);
+    InjectedConsts32 k;
+    k.dt = (float)dt;
+    k.root_dt = (float)std::sqrt(dt);
+    k.m0 = (float)p->rho;
+    k.m1 = (float)std::sqrt(1.0 - p->rho * p->rho);
+    k.mu = (float)p->mu;
+    k.kappa = (float)p->kappa;
+    k.v_bar = (float)p->v_bar;
+    k.sigma_v = (float)p->sigma_v;
+    k.x0 = (float)p->x0;
+    k.v0 = (float)p->v0;
+    CB_CUDA(launch_heston_injected_f32(d_Z, k, R, N, d_x, d_v, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_heston_terminal_injected_f64(cb_ctx *c, const double *d_Z, const cb_heston_params *p, uint64_t R,
+                                               uint32_t N, double *d_x, double *d_v) {
+    CB_CTX(c);
+    int rc = check_heston(p, R, N);
+    if (rc) return rc;
+    CB_REQUIRE(d_Z && d_x && d_v, "NULL device pointer");
+    const double dt = p->T / (double)(N - 1);
+    InjectedConsts64 k;
+    k.dt = dt;
+    k.root_dt = std::sqrt(dt);
+    k.m0 = p->rho;
+    k.m1 = std::sqrt(1.0 - p->rho * p->rho);
+    k.mu = p->mu;
+    k.kappa = p->kappa;
+    k.v_bar = p->v_bar;
+    k.sigma_v = p->sigma_v;
+    k.x0 = p->x0;
+    k.v0 = p->v0;
+    CB_CUDA(launch_heston_injected_f64(d_Z, k, R, N, d_x, d_v, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_heston_terminal_injected_host_f32(cb_ctx *c, const float *h_Z, const cb_heston_params *p,
+                                                    uint64_t R, uint32_t N, float *h_x, float *h_v) {
+    CB_CTX(c);
+    int rc = check_heston(p, R, N);
+    if (rc) return rc;
+    CB_REQUIRE(h_Z && h_x && h_v, "NULL host pointer");
+    const uint64_t H = (R + 1) / 2;
+    const size_t z_bytes = sizeof(float) * 2 * H * (size_t)(N - 1);
+    const size_t out_bytes = sizeof(float) * R;
+    const size_t z_pad = (z_bytes + 255) & ~(size_t)255, o_pad = (out_bytes + 255) & ~(size_t)255;
+    rc = ensure_scratch(c, z_pad + 2 * o_pad);
+    if (rc) return rc;
+    float *d_Z = (float *)c->scratch;
+    float *d_x = (float *)((char *)c->scratch + z_pad);
+    float *d_v = (float *)((char *)c->scratch + z_pad + o_pad);
+    CB_CUDA(cudaMemcpyAsync(d_Z, h_Z, z_bytes, cudaMemcpyHostToDevice, c->stream));
+    rc = cb_heston_terminal_injected_f32(c, d_Z, p, R, N, d_x, d_v);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(h_x, d_x, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaMemcpyAsync(h_v, d_v, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------- Heston: fused kernel
+
+template <typename real>
+static FusedConsts<real> make_consts(const cb_heston_params *p, uint64_t R, uint32_t N, const double *strikes, int nK,
+                                     uint64_t seed, uint32_t subsequence, uint64_t pair_first, uint64_t pair_count) {
+    FusedConsts<real> k;
+    const double dt = p->T / (double)(N - 1);
+    k.drift_v = (real)(-0.5 * dt);
+    k.decay = (real)(1.0 - p->kappa * dt);
+    k.pull = (real)(p->kappa * p->v_bar * dt);
+    k.w0 = (real)(p->sigma_v * p->rho);
+    k.w1 = (real)(p->sigma_v * std::sqrt(1.0 - p->rho * p->rho));
+    k.v0 = (real)p->v0;
+    k.x0 = (real)p->x0;
+    k.mu_dt = (real)(p->mu * dt);
+    k.floor_v = (real)1.1920928955078125e-07f;
+    k.neg2ln2_dt = (float)(-2.0 * 0.6931471805599453 * dt);
+    k.steps = N - 1;
+    k.subsequence = subsequence;
+    k.pair_first = pair_first;
+    k.pair_count = pair_count;
+    k.partnered = R / 2;
+    k.nK = nK;
+    k.keys = philox_keys_from_seed(seed);
+    for (int i = 0; i < kMaxStrikes; ++i) k.strikes[i] = (real)(i < nK ? strikes[i] : 0.0);
+    return k;
+}
+
+// Wave-aware geometry: with W = ceil(pairs / (threads*ppt)) block-sized work items and
+// at most sm*bps resident blocks, pick the residency (>= 60% of the maximum) whose
+// last wave is fullest; every thread then runs the same number of iterations.
+template <typename real>
+static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, LaunchShape *s) {
+    const int threads = c->threads ? c->threads : 128;
+    const int ppt = traj ? 4 : (c->ppt ? c->ppt : 1);
+    const auto key = std::make_tuple((int)(sizeof(real) == 8), traj ? -4 : ppt, (int)multi, threads);
+    auto it = c->occ_cache.find(key);
+    if (it == c->occ_cache.end()) {
+        int bps = 0, regs = 0;
+        CB_CUDA((fused_occupancy<real>(threads, traj ? -4 : ppt, multi, &bps, &regs)));
+        it = c->occ_cache.emplace(key, std::make_pair(bps, regs)).first;
+    }
+    int bps = it->second.first;
+    CB_REQUIRE(bps >= 1, "fused kernel does not fit on an SM with %d threads", threads);
+    if (c->blocks_per_sm > 0) bps = std::min(bps, c->blocks_per_sm);
+    const uint64_t per_block = (uint64_t)threads * ppt;
+    const uint64_t items = std::max<uint64_t>(1, (pair_count + per_block - 1) / per_block);
+    const uint64_t resident = (uint64_t)c->sm_count * bps;
+    uint64_t blocks;
+    if (items <= resident) {
+        blocks = items;
+    } else if (c->blocks_per_sm > 0) {
+        blocks = resident;
+    } else {
+        double best = -1.0;
+        blocks = resident;
+        for (int b = bps; b >= std::max(1, (int)std::ceil(0.6 * bps)); --b) {
+            const uint64_t g = (uint64_t)c->sm_count * b;
+            const uint64_t waves = (items + g - 1) / g;
+            // time ~ waves * b (a wave of b blocks/SM takes ~b units once the pipe is saturated)
+            const double eff = (double)items / ((double)waves * (double)g);
+            if (eff > best + 1e-9) {
+                best = eff;
+                blocks = g;
+            }
+        }
+    }
+    blocks = std::min<uint64_t>(blocks, kMaxGridBlocks);
+    s->threads = threads;
+    s->blocks = (int)blocks;
+    s->pairs_per_thread = ppt;
+    return CB_OK;
+}
+
+template <typename real>
+static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N, const double *h_strikes,
+                               int nK, uint64_t seed, uint32_t subsequence, uint64_t pair_first, uint64_t pair_count,
+                               cb_comm *comm, real *d_x, real *d_v, real *d_traj) {
+    CB_CTX(c);
+    int rc = check_heston(p, R, N);
+    if (rc) return rc;
+    CB_REQUIRE(h_strikes != nullptr, "h_strikes is NULL");
+    CB_REQUIRE(nK >= 1 && nK <= CB_MAX_STRIKES, "nK must be in [1,%d]", CB_MAX_STRIKES);
+    const uint64_t H = (R + 1) / 2;
+    CB_REQUIRE(pair_first <= H && pair_count <= H - pair_first, "pair range [%llu,+%llu) outside [0,%llu)",
+               (unsigned long long)pair_first, (unsigned long long)pair_count, (unsigned long long)H);
+    CB_REQUIRE((d_x == nullptr) == (d_v == nullptr), "d_x and d_v must both be given or both be NULL");
+    if (comm != nullptr) {
+        rc = need_nccl();
+        if (rc) return rc;
+    }
+    const FusedConsts<real> k = make_consts<real>(p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count);
+    if (pair_count > 0) {
+        LaunchShape shape;
+        rc = choose_shape<real>(c, pair_count, nK > 1, d_traj != nullptr, &shape);
+        if (rc) return rc;
+        CB_CUDA(launch_heston_fused<real>(k, shape, c->ws, d_x, d_v, d_traj, c->stream));
+    } else {
+        CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));   // an empty shard adds nothing
+    }
+    if (comm != nullptr)
+        CB_NCCL(g_nccl.AllReduce(c->ws.result, c->ws.result, (size_t)2 * nK, ncclDouble, ncclSum, comm->comm,
+                                 c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_heston_price_launch_f32(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                          const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                          uint64_t pair_first, uint64_t pair_count, cb_comm *comm, float *d_x,
+                                          float *d_v, float *d_traj) {
+    return heston_price_launch<float>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm, d_x,
+                                      d_v, d_traj);
+}
+
+extern "C" CB_API int cb_heston_price_launch_f64(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                          const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                          uint64_t pair_first, uint64_t pair_count, cb_comm *comm, double *d_x,
+                                          double *d_v, double *d_traj) {
+    return heston_price_launch<double>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm,
+                                       d_x, d_v, d_traj);
+}
+
+extern "C" CB_API int cb_heston_price_finish(cb_ctx *c, int nK, double *h_sum, double *h_sumsq) {
+    CB_CTX(c);
+    CB_REQUIRE(nK >= 1 && nK <= CB_MAX_STRIKES, "nK must be in [1,%d]", CB_MAX_STRIKES);
+    CB_REQUIRE(h_sum != nullptr && h_sumsq != nullptr, "NULL output");
+    CB_CUDA(cudaMemcpyAsync(c->h_result, c->ws.result, sizeof(double) * 2 * nK, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(h_sum, c->h_result, sizeof(double) * nK);
+    memcpy(h_sumsq, c->h_result + nK, sizeof(double) * nK);
+    return CB_OK;
+}
+
+template <typename real>
+static int payoff_sums(cb_ctx *c, const real *d_x, uint64_t R, const double *h_strikes, int nK, double *h_sum,
+                       double *h_sumsq) {
+    CB_CTX(c);
+    CB_REQUIRE(d_x != nullptr && h_strikes != nullptr, "NULL argument");
+    CB_REQUIRE(R >= 1, "R must be >= 1");
+    CB_REQUIRE(nK >= 1 && nK <= CB_MAX_STRIKES, "nK must be in [1,%d]", CB_MAX_STRIKES);
+    CB_CUDA(launch_call_payoff_sums<real>(d_x, R, h_strikes, nK, c->ws, c->sm_count, c->stream));
+    return cb_heston_price_finish(c, nK, h_sum, h_sumsq);
+}
+
+extern "C" CB_API int cb_call_payoff_sums_f32(cb_ctx *c, const float *d_x, uint64_t R, const double *h_strikes, int nK,
+                                       double *h_sum, double *h_sumsq) {
+    return payoff_sums<float>(c, d_x, R, h_strikes, nK, h_sum, h_sumsq);
+}
+
+extern "C" CB_API int cb_call_payoff_sums_f64(cb_ctx *c, const double *d_x, uint64_t R, const double *h_strikes, int nK,
+                                       double *h_sum, double *h_sumsq) {
+    return payoff_sums<double>(c, d_x, R, h_strikes, nK, h_sum, h_sumsq);
+}
+
+// ---------------------------------------------------------------- pi
+
+extern "C" CB_API int cb_pi_count_launch(cb_ctx *c, uint64_t n, uint64_t seed, uint32_t subsequence, int antithetic,
+                                  uint64_t draw_first, uint64_t draw_count, cb_comm *comm) {
+    CB_CTX(c);
+    const uint64_t ndraw = antithetic ? (n + 1) / 2 : n;
+    CB_REQUIRE(draw_first <= ndraw && draw_count <= ndraw - draw_first, "draw range outside [0,%llu)",
+               (unsigned long long)ndraw);
+    if (comm != nullptr) {
+        int rc = need_nccl();
+        if (rc) return rc;
+    }
+    CB_CUDA(launch_pi_count(n, antithetic, draw_first, draw_count, philox_keys_from_seed(seed), subsequence,
+                            c->d_inside, c->sm_count, c->stream));
+    if (comm != nullptr)
+        CB_NCCL(g_nccl.AllReduce(c->d_inside, c->d_inside, 1, ncclUint64, ncclSum, comm->comm, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_pi_count_finish(cb_ctx *c, uint64_t *h_inside) {
+    CB_CTX(c);
+    CB_REQUIRE(h_inside != nullptr, "h_inside is NULL");
+    unsigned long long *h = reinterpret_cast<unsigned long long *>(c->h_result + kMaxAcc);
+    CB_CUDA(cudaMemcpyAsync(h, c->d_inside, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    *h_inside = *h;
+    return CB_OK;
+}
+
+// ---------------------------------------------------------------- calibration
+
+extern "C" CB_API int cb_peak_measure(cb_ctx *c, int kind, int repeats, double *ops_per_s, float *ms_best) {
+    CB_CTX(c);
+    CB_REQUIRE(ops_per_s != nullptr, "ops_per_s is NULL");
+    CB_REQUIRE(kind >= 0 && kind <= 10, "kind must be in [0,10]");
+    if (repeats < 1) repeats = 1;
+    size_t bytes = 4096;
+    if (kind == 8 || kind == 10) bytes = (size_t)4 << 30;   // far larger than the 126 MB L2
+    void *scratch = nullptr;
+    CB_CUDA(cudaMalloc(&scratch, bytes));
+    float best = 1e30f;
+    double work = 0.0;
+    int rc = CB_OK;
+    for (int r = 0; r < repeats + 1; ++r) {   // first pass is a warm-up
+        cudaEventRecord(c->ev_start, c->stream);
+        cudaError_t e = launch_peak_kernel(kind, c->sm_count, scratch, bytes, &work, c->stream);
+        cudaEventRecord(c->ev_stop, c->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(c->ev_stop);
+        if (e != cudaSuccess) {
+            rc = fail(CB_ERR_CUDA, "peak kernel %d failed: %s", kind, cudaGetErrorString(e));
+            break;
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaFree(scratch);
+    if (rc) return rc;
+    *ops_per_s = work / ((double)best * 1e-3);
+    if (ms_best) *ms_best = best;
+    return CB_OK;
+}

@@ -1,0 +1,92 @@
+// Internal launch interface between capi.cu and the kernel translation units.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/cocos_b200.h"
+#include "philox.cuh"
+
+namespace cb {
+
+constexpr int kMaxStrikes = CB_MAX_STRIKES;
+constexpr int kMaxAcc = 2 * kMaxStrikes;          // sums then sums of squares
+constexpr int kMaxGridBlocks = 148 * 32 * 2;      // workspace rows for per-block partials
+
+// launch geometry chosen by the host for one fused launch
+struct LaunchShape {
+    int threads;            // per block
+    int blocks;             // grid
+    int pairs_per_thread;   // 1, 2 or 4 interleaved pairs per thread
+};
+
+// Launch-uniform constants of the fused kernels, precomputed in double on the host.
+template <typename real>
+struct FusedConsts {
+    real drift_v;        // -0.5*dt                 x += drift_v*v + sqrt(v)*dB0   (mu*dt is added once, see x_shift)
+    real decay;          // 1 - kappa*dt            v  = decay*v + pull + sqrt(v)*w
+    real pull;           // kappa*v_bar*dt
+    real w0, w1;         // sigma_v*rho, sigma_v*sqrt(1-rho^2)   w = w0*dB0 + w1*dB1
+    real v0;
+    real x0;
+    real mu_dt;          // mu*dt (trajectory rows and the final shift use it)
+    real floor_v;        // float32 eps, also for double state (heston_utilities.py:91)
+    float neg2ln2_dt;    // -2 ln2 * dt: MUFU.LG2 output -> (r*sqrt(dt))^2
+    uint32_t steps;      // N-1 Euler steps
+    uint32_t subsequence;
+    uint64_t pair_first; // shard
+    uint64_t pair_count;
+    uint64_t partnered;  // floor(R/2): pairs with global index < partnered own two paths
+    int nK;
+    PhiloxKeys keys;
+    real strikes[kMaxStrikes];
+};
+
+struct ReduceWorkspace {
+    double *partials;    // [kMaxGridBlocks][kMaxAcc]
+    unsigned int *ticket;
+    double *result;      // [kMaxAcc]: sums[nK] then sumsq[nK]
+};
+
+template <typename real>
+cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &shape, ReduceWorkspace ws,
+                                real *d_x, real *d_v, real *d_traj, cudaStream_t stream);
+
+template <typename real>
+cudaError_t fused_occupancy(int threads, int pairs_per_thread, bool multi, int *blocks_per_sm, int *regs);
+
+// parity kernels (reference operation order, injected normals)
+struct InjectedConsts32 {
+    float dt, root_dt, m0, m1, mu, kappa, v_bar, sigma_v, x0, v0;
+};
+struct InjectedConsts64 {
+    double dt, root_dt, m0, m1, mu, kappa, v_bar, sigma_v, x0, v0;
+};
+cudaError_t launch_heston_injected_f32(const float *d_Z, const InjectedConsts32 &c, uint64_t R, uint32_t N,
+                                       float *d_x, float *d_v, cudaStream_t stream);
+cudaError_t launch_heston_injected_f64(const double *d_Z, const InjectedConsts64 &c, uint64_t R, uint32_t N,
+                                       double *d_x, double *d_v, cudaStream_t stream);
+
+// payoff reduction over a device array of terminal log prices
+template <typename real>
+cudaError_t launch_call_payoff_sums(const real *d_x, uint64_t R, const double *strikes, int nK,
+                                    ReduceWorkspace ws, int sm_count, cudaStream_t stream);
+
+// random arrays
+cudaError_t launch_philox_words(uint32_t *d_out, uint64_t n_blocks, uint64_t first, uint32_t block,
+                                const PhiloxKeys &k, uint32_t subseq, cudaStream_t s);
+template <typename real, bool NORMAL>
+cudaError_t launch_random_fill(real *d_out, uint64_t n, const PhiloxKeys &k, uint32_t subseq, cudaStream_t s);
+template <typename real, bool NORMAL>
+cudaError_t launch_random_antithetic(real *d_out, uint64_t outer, uint64_t d_axis, uint64_t inner,
+                                     const PhiloxKeys &k, uint32_t subseq, cudaStream_t s);
+
+// Monte-Carlo pi
+cudaError_t launch_pi_count(uint64_t n, int antithetic, uint64_t draw_first, uint64_t draw_count,
+                            const PhiloxKeys &k, uint32_t subseq, unsigned long long *d_inside,
+                            int sm_count, cudaStream_t s);
+
+// calibration
+cudaError_t launch_peak_kernel(int kind, int sm_count, void *d_scratch, size_t scratch_bytes, double *work_done,
+                               cudaStream_t s);
+
+}  // namespace cb

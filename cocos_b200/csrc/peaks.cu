@@ -1,0 +1,141 @@
+// Pipe-peak calibration kernels: the roofline denominators MEASURED_PEAKS.json lacks
+// (FP32 FMA, MUFU, FP64, INT/Philox issue, HBM write), SURVEY.md section 8d step 0.
+// Each thread runs 8 independent dependency chains so the pipe, not latency, is timed.
+#include "kernels.h"
+
+namespace cb {
+
+constexpr int kChains = 8;
+constexpr int kIters = 4096;
+
+template <int KIND>
+__device__ __forceinline__ float chain_op(float x, float a, float b) {
+    if constexpr (KIND == 0) return fmaf(x, a, b);
+    else if constexpr (KIND == 1) return mufu_lg2(x) + 6.0f;     // stays in [6,9]; the FADD is on another pipe
+    else if constexpr (KIND == 2) return mufu_sqrt(x);
+    else if constexpr (KIND == 3) return mufu_sin(x);
+    else if constexpr (KIND == 4) return mufu_ex2(x) * 0.25f;
+    else return mufu_rsqrt(x);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+peak_f32_kernel(float *out, float a, float b) {
+    float x[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) x[i] = 1.0f + 0.001f * (float)(threadIdx.x + i);
+#pragma unroll 1
+    for (int it = 0; it < kIters; it += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) x[i] = chain_op<KIND>(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s;   // never true in practice; keeps the chains alive
+}
+
+__global__ void __launch_bounds__(256)
+peak_f64_kernel(double *out, double a, double b) {
+    double x[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) x[i] = 1.0 + 0.001 * (double)(threadIdx.x + i);
+#pragma unroll 1
+    for (int it = 0; it < kIters; it += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) x[i] = fma(x[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256)
+peak_philox_kernel(uint32_t *out, const __grid_constant__ PhiloxKeys k) {
+    uint32_t acc = 0;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < kIters / 4; it += 2) {
+        const uint4 a = philox4x32_10(tid, it, 0u, 1u, k);
+        const uint4 b = philox4x32_10(tid, it + 1, 0u, 1u, k);
+        acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w;
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+peak_alu_kernel(uint32_t *out, uint32_t a, uint32_t b) {
+    uint32_t x[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) x[i] = threadIdx.x * 2654435761u + i;
+#pragma unroll 1
+    for (int it = 0; it < kIters; it += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) x[i] = (x[i] | a) ^ x[(i + 1) % kChains];   // one LOP3 each
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s ^= x[i];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256)
+peak_hbm_write_kernel(float4 *out, size_t n_vec) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float v = (float)threadIdx.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride)
+        __stcs(out + i, make_float4(v, v, v, v));
+}
+
+__global__ void __launch_bounds__(256)
+peak_hbm_copy_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n_vec) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride)
+        __stcs(out + i, __ldcs(in + i));
+}
+
+cudaError_t launch_peak_kernel(int kind, int sm_count, void *d_scratch, size_t scratch_bytes, double *work_done,
+                               cudaStream_t s) {
+    const int threads = 256, grid = sm_count * 8;
+    const double thread_ops = (double)grid * threads * kIters * kChains;
+    switch (kind) {
+        case 0: peak_f32_kernel<0><<<grid, threads, 0, s>>>((float *)d_scratch, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 1: peak_f32_kernel<1><<<grid, threads, 0, s>>>((float *)d_scratch, 0.f, 0.f); *work_done = thread_ops; break;
+        case 2: peak_f32_kernel<2><<<grid, threads, 0, s>>>((float *)d_scratch, 0.f, 0.f); *work_done = thread_ops; break;
+        case 3: peak_f32_kernel<3><<<grid, threads, 0, s>>>((float *)d_scratch, 0.f, 0.f); *work_done = thread_ops; break;
+        case 4: peak_f32_kernel<4><<<grid, threads, 0, s>>>((float *)d_scratch, 0.f, 0.f); *work_done = thread_ops; break;
+        case 5: peak_f32_kernel<5><<<grid, threads, 0, s>>>((float *)d_scratch, 0.f, 0.f); *work_done = thread_ops; break;
+        case 6: peak_f64_kernel<<<grid, threads, 0, s>>>((double *)d_scratch, 1.000001, 1e-7); *work_done = thread_ops; break;
+        case 7: {
+            const PhiloxKeys k = philox_keys_from_seed(0x1234567ull);
+            peak_philox_kernel<<<grid, threads, 0, s>>>((uint32_t *)d_scratch, k);
+            *work_done = (double)grid * threads * (kIters / 4);   // Philox calls
+            break;
+        }
+        case 8: {
+            const size_t n_vec = scratch_bytes / 16;
+            peak_hbm_write_kernel<<<sm_count * 16, threads, 0, s>>>((float4 *)d_scratch, n_vec);
+            *work_done = (double)n_vec * 16.0;
+            break;
+        }
+        case 9: peak_alu_kernel<<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0x9E3779B9u, 0x01010101u); *work_done = thread_ops; break;
+        case 10: {
+            const size_t n_vec = scratch_bytes / 32;
+            peak_hbm_copy_kernel<<<sm_count * 16, threads, 0, s>>>((const float4 *)d_scratch,
+                                                                   (float4 *)d_scratch + n_vec, n_vec);
+            *work_done = (double)n_vec * 32.0;
+            break;
+        }
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace cb

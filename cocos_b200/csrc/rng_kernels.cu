@@ -1,0 +1,187 @@
+// Random-array kernels behind cocos.numerics.random's array API (HBM-write bound).
+//
+//   rand / randn                   cocos/numerics/random.py:127-153 (af.data.randu / af.data.randn)
+//   randn_antithetic               cocos/numerics/random.py:190-216
+//   rand_antithetic                cocos/numerics/random.py:219-245
+//
+// Element order (CPU model: oracle/philox_numpy.py rand_f32 / randn_f32_model / ...):
+//   f32: elements 4j..4j+3 come from the four words of Philox(index=j, block=0, subsequence)
+//        uniform: u01(o0..o3); normal: Box-Muller(o0,o1) -> (4j, 4j+1), Box-Muller(o2,o3) -> (4j+2, 4j+3)
+//   f64: elements 2j, 2j+1 from Philox(index=j): uniform u52(o0,o1), u52(o2,o3);
+//        normal: one Box-Muller pair from U = 1-u52(o0,o1), t = u52(o2,o3)
+// Each thread produces 16 bytes per Philox call and stores them as one vector.
+#include "kernels.h"
+
+namespace cb {
+
+template <typename real, bool NORMAL>
+struct Draw;   // fills v[0..W) from one Philox block
+
+template <>
+struct Draw<float, false> {
+    static constexpr int W = 4;
+    static __device__ __forceinline__ void make(const uint4 &o, float (&v)[4]) {
+        v[0] = u01_f32(o.x); v[1] = u01_f32(o.y); v[2] = u01_f32(o.z); v[3] = u01_f32(o.w);
+    }
+    static __device__ __forceinline__ float reflect(float u) { return __fsub_rn(1.0f, u); }
+};
+template <>
+struct Draw<float, true> {
+    static constexpr int W = 4;
+    static __device__ __forceinline__ void make(const uint4 &o, float (&v)[4]) {
+        box_muller(o.x, o.y, -1.3862943611198906f /* -2 ln 2 */, kTwoPi, v[0], v[1]);
+        box_muller(o.z, o.w, -1.3862943611198906f, kTwoPi, v[2], v[3]);
+    }
+    static __device__ __forceinline__ float reflect(float z) { return -z; }
+};
+template <>
+struct Draw<double, false> {
+    static constexpr int W = 2;
+    static __device__ __forceinline__ void make(const uint4 &o, double (&v)[2]) {
+        v[0] = u01_f64(o.x, o.y); v[1] = u01_f64(o.z, o.w);
+    }
+    static __device__ __forceinline__ double reflect(double u) { return 1.0 - u; }
+};
+template <>
+struct Draw<double, true> {
+    static constexpr int W = 2;
+    static __device__ __forceinline__ void make(const uint4 &o, double (&v)[2]) {
+        const double U = 1.0 - u01_f64(o.x, o.y);              // (0,1]
+        const double t = u01_f64(o.z, o.w);                    // [0,1)
+        const double r = sqrt(-2.0 * log(U));
+        double s, c;
+        sincospi(2.0 * t - 1.0, &s, &c);                       // theta = 2 pi t - pi
+        v[0] = r * c;
+        v[1] = r * s;
+    }
+    static __device__ __forceinline__ double reflect(double z) { return -z; }
+};
+
+__global__ void __launch_bounds__(256)
+philox_words_kernel(uint4 *__restrict__ out, uint64_t n_blocks, uint64_t first, uint32_t block,
+                    const __grid_constant__ PhiloxKeys k, uint32_t subseq) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_blocks; i += stride) {
+        const uint64_t idx = first + i;
+        out[i] = philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), block, subseq, k);
+    }
+}
+
+template <typename real, bool NORMAL>
+__global__ void __launch_bounds__(256)
+random_fill_kernel(real *__restrict__ out, uint64_t n, const __grid_constant__ PhiloxKeys k, uint32_t subseq) {
+    using D = Draw<real, NORMAL>;
+    constexpr int W = D::W;
+    const uint64_t n_blocks = (n + W - 1) / W;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_blocks; j += stride) {
+        real v[W];
+        D::make(philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, subseq, k), v);
+        const uint64_t base = j * W;
+        if (aligned && base + W <= n) {
+            if constexpr (W == 4) __stcs(reinterpret_cast<float4 *>(out + base), make_float4(v[0], v[1], v[2], v[3]));
+            else __stcs(reinterpret_cast<double2 *>(out + base), make_double2(v[0], v[1]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < W; ++e) if (base + e < n) out[base + e] = v[e];
+        }
+    }
+}
+
+// Output shape (outer, d, inner) row-major, antithetic along the middle axis:
+// draws fill [.., 0:ceil(d/2), ..] in draw order (flattened (outer, ceil(d/2), inner)),
+// reflections fill [.., ceil(d/2):d, ..].
+template <typename real, bool NORMAL>
+__global__ void __launch_bounds__(256)
+random_antithetic_kernel(real *__restrict__ out, uint64_t outer, uint64_t d, uint64_t inner,
+                         const __grid_constant__ PhiloxKeys k, uint32_t subseq) {
+    using D = Draw<real, NORMAL>;
+    constexpr int W = D::W;
+    const uint64_t da = (d + 1) / 2, df = d / 2;
+    const uint64_t slab = da * inner;                 // draws per outer index
+    const uint64_t n_draw = outer * slab;
+    const uint64_t n_blocks = (n_draw + W - 1) / W;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    // fast path (outer == 1, e.g. the Heston (R,2) draw): draw g lands at g, its reflection at slab+g
+    const bool vec = (outer == 1) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                     ((slab * sizeof(real)) % 16 == 0);
+    const uint64_t n_mirrored = df * inner;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_blocks; j += stride) {
+        real v[W];
+        D::make(philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, subseq, k), v);
+        const uint64_t base = j * W;
+        if (vec && base + W <= n_draw) {
+            if constexpr (W == 4) __stcs(reinterpret_cast<float4 *>(out + base), make_float4(v[0], v[1], v[2], v[3]));
+            else __stcs(reinterpret_cast<double2 *>(out + base), make_double2(v[0], v[1]));
+            if (base + W <= n_mirrored) {
+                if constexpr (W == 4)
+                    __stcs(reinterpret_cast<float4 *>(out + slab + base),
+                           make_float4(D::reflect(v[0]), D::reflect(v[1]), D::reflect(v[2]), D::reflect(v[3])));
+                else
+                    __stcs(reinterpret_cast<double2 *>(out + slab + base),
+                           make_double2(D::reflect(v[0]), D::reflect(v[1])));
+            } else {
+#pragma unroll
+                for (int e = 0; e < W; ++e) if (base + e < n_mirrored) out[slab + base + e] = D::reflect(v[e]);
+            }
+            continue;
+        }
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+            const uint64_t g = base + e;
+            if (g >= n_draw) break;
+            const uint64_t o = g / slab, rem = g % slab;
+            const uint64_t a = rem / inner, in = rem % inner;
+            const uint64_t dst = (o * d + a) * inner + in;
+            out[dst] = v[e];
+            if (a < df) out[dst + da * inner] = D::reflect(v[e]);
+        }
+    }
+}
+
+static int fill_grid(uint64_t n_blocks) {
+    uint64_t b = (n_blocks + 255) / 256;
+    if (b < 1) b = 1;
+    const uint64_t cap = 148ull * 8 * 4;
+    return (int)(b > cap ? cap : b);
+}
+
+cudaError_t launch_philox_words(uint32_t *d_out, uint64_t n_blocks, uint64_t first, uint32_t block,
+                                const PhiloxKeys &k, uint32_t subseq, cudaStream_t s) {
+    if (n_blocks == 0) return cudaSuccess;
+    philox_words_kernel<<<fill_grid(n_blocks), 256, 0, s>>>(reinterpret_cast<uint4 *>(d_out), n_blocks, first, block,
+                                                           k, subseq);
+    return cudaGetLastError();
+}
+
+template <typename real, bool NORMAL>
+cudaError_t launch_random_fill(real *d_out, uint64_t n, const PhiloxKeys &k, uint32_t subseq, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    constexpr int W = Draw<real, NORMAL>::W;
+    random_fill_kernel<real, NORMAL><<<fill_grid((n + W - 1) / W), 256, 0, s>>>(d_out, n, k, subseq);
+    return cudaGetLastError();
+}
+
+template <typename real, bool NORMAL>
+cudaError_t launch_random_antithetic(real *d_out, uint64_t outer, uint64_t d_axis, uint64_t inner,
+                                     const PhiloxKeys &k, uint32_t subseq, cudaStream_t s) {
+    const uint64_t n_draw = outer * ((d_axis + 1) / 2) * inner;
+    if (n_draw == 0) return cudaSuccess;
+    constexpr int W = Draw<real, NORMAL>::W;
+    random_antithetic_kernel<real, NORMAL><<<fill_grid((n_draw + W - 1) / W), 256, 0, s>>>(d_out, outer, d_axis,
+                                                                                           inner, k, subseq);
+    return cudaGetLastError();
+}
+
+#define CB_INSTANTIATE(real, normal)                                                                              \
+    template cudaError_t launch_random_fill<real, normal>(real *, uint64_t, const PhiloxKeys &, uint32_t,          \
+                                                          cudaStream_t);                                          \
+    template cudaError_t launch_random_antithetic<real, normal>(real *, uint64_t, uint64_t, uint64_t,              \
+                                                                const PhiloxKeys &, uint32_t, cudaStream_t);
+CB_INSTANTIATE(float, false)
+CB_INSTANTIATE(float, true)
+CB_INSTANTIATE(double, false)
+CB_INSTANTIATE(double, true)
+
+}  // namespace cb

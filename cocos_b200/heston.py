@@ -1,0 +1,185 @@
+"""Heston pricing entry points: examples/stochastic_volatility/heston_utilities.py on B200.
+
+Same names, arguments and return types as the reference:
+  simulate_heston_model                         heston_utilities.py:24-96
+  compute_option_price_from_simulated_paths     heston_utilities.py:99-119
+  simulate_and_compute_option_price             heston_utilities.py:122-164   (the map function)
+  simulate_and_compute_option_price_gpu         heston_utilities.py:217-270
+plus what the fused kernel gives for free: standard errors from antithetic pair
+averages, a strike sweep over shared paths (BASELINE config 5), float64 state and the
+full log-price trajectory.  The reference's Python time loop (N-1 iterations of ~21
+array operations) is replaced by ONE kernel launch.
+"""
+import ctypes
+import math
+import typing as tp
+
+import numpy as np
+
+from . import _lib
+from .device import ComputeDeviceManager, current_context
+from .multi_processing.device_pool import ComputeDevicePool
+from .numerics import random as _random
+from .numerics._array import empty_on, ndarray
+from .numerics.numerical_package_bundle import B200Bundle, NumericalPackageBundle
+
+_SUFFIX = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
+
+
+def _require_b200(bundle):
+    if bundle is not None and not (isinstance(bundle, type) and issubclass(bundle, B200Bundle)):
+        raise TypeError("cocos_b200 runs the Heston path on the B200 bundle only (B200Bundle / CocosBundle); "
+                        "the NumPy restatement is test infrastructure under oracle/")
+
+
+def _params(T, mu, kappa, v_bar, sigma_v, rho, x0, v0) -> "_lib.HestonParams":
+    return _lib.HestonParams(float(T), float(mu), float(kappa), float(v_bar), float(sigma_v), float(rho),
+                             float(x0), float(v0))
+
+
+def _suffix(dtype) -> str:
+    try:
+        return _SUFFIX[np.dtype(dtype)]
+    except (KeyError, TypeError):
+        raise TypeError(f"dtype {dtype} is not supported (float32 and float64 are)") from None
+
+
+def simulate_heston_model(T: float, N: int, R: int, mu: float, kappa: float, v_bar: float, sigma_v: float,
+                          rho: float, x0: float, v0: float,
+                          numerical_package_bundle: tp.Optional[tp.Type[NumericalPackageBundle]] = B200Bundle,
+                          dtype=np.float32, return_trajectory: bool = False) -> tp.Tuple:
+    """Simulate R antithetic Heston paths over N time points (N-1 Euler-Maruyama steps).
+
+    Returns device arrays (x_T, v_T), each of shape (R,): path i < ceil(R/2) and path
+    i + ceil(R/2) are antithetic partners (the reference's layout, random.py:199-214).
+    With ``return_trajectory`` a third array of shape (N, 2*ceil(R/2)) holds every
+    path's log price at every time point (row 0 = x0; the last column of an odd R is unused).
+    """
+    _require_b200(numerical_package_bundle)
+    R, N = int(R), int(N)
+    if R < 1:
+        raise ValueError("R must be >= 1")
+    ctx = current_context()
+    sfx = _suffix(dtype)
+    pairs = (R + 1) // 2
+    # shard layout [pairs | partners]: one contiguous buffer, the first R entries are the reference layout
+    x = empty_on(ctx, (2 * pairs,), dtype)
+    v = empty_on(ctx, (2 * pairs,), dtype)
+    traj = empty_on(ctx, (N, 2 * pairs), dtype) if return_trajectory else None
+    p = _params(T, mu, kappa, v_bar, sigma_v, rho, x0, v0)
+    k_arr, nK = _lib.strikes_array([1.0])
+    launch = getattr(_lib.lib(), f"cb_heston_price_launch_{sfx}")
+    _lib.check(launch(ctx.handle, ctypes.byref(p), R, N, k_arr, nK, _random.get_seed(), _random.next_subsequence(),
+                      0, pairs, None, x.data_ptr, v.data_ptr, traj.data_ptr if traj is not None else None))
+    out = (x[:R], v[:R])
+    return out + (traj,) if return_trajectory else out
+
+
+def call_payoff_sums(x_simulated: ndarray, strikes: tp.Sequence[float]) -> tp.Tuple[np.ndarray, np.ndarray]:
+    """(sum of payoffs, sum of squared antithetic-unit averages) per strike, undiscounted."""
+    if not isinstance(x_simulated, ndarray):
+        raise TypeError("x_simulated must be a cocos_b200 device array (no CPU branch)")
+    ctx = _lib.context(x_simulated.device_id)
+    k_arr, nK = _lib.strikes_array(strikes)
+    sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+    fn = getattr(_lib.lib(), f"cb_call_payoff_sums_{_suffix(x_simulated.dtype)}")
+    if not x_simulated.tensor.is_contiguous():
+        raise ValueError("x_simulated must be contiguous")
+    _lib.check(fn(ctx.handle, x_simulated.data_ptr, x_simulated.size, k_arr, nK, sums, sumsq))
+    return np.array(sums), np.array(sumsq)
+
+
+def compute_option_price_from_simulated_paths(
+        r: float, T: float, K: float, x_simulated,
+        numerical_package_bundle: tp.Optional[tp.Type[NumericalPackageBundle]] = B200Bundle) -> float:
+    """exp(-rT) * mean(max(exp(x_T) - K, 0)) over a device array of terminal log prices."""
+    _require_b200(numerical_package_bundle)
+    sums, _ = call_payoff_sums(x_simulated, [K])
+    return float(math.exp(-r * T) * sums[0] / x_simulated.size)
+
+
+def _price_from_sums(r, T, R, sums, sumsq):
+    """Discounted prices and standard errors (from antithetic pair averages) per strike."""
+    disc = math.exp(-r * T)
+    units = (R + 1) // 2
+    sums, sumsq = np.asarray(sums, dtype=np.float64), np.asarray(sumsq, dtype=np.float64)
+    price = disc * sums / R
+    mean_unit = sums / (2.0 * units) if R % 2 == 0 else sums / R      # odd R: the lone unit is O(1/R)
+    var_unit = np.maximum(sumsq / units - mean_unit ** 2, 0.0)
+    se = disc * np.sqrt(var_unit / max(units - 1, 1))
+    return price, se
+
+
+def heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, strikes, dtype=np.float32,
+                       compute_device_pool: tp.Optional[ComputeDevicePool] = None):
+    """One fused launch per device: undiscounted payoff sums for every strike."""
+    R, nT = int(R), int(nT)
+    p = _params(T, r, kappa, v_bar, sigma_v, rho, x0, v0)
+    seed, sub = _random.get_seed(), _random.next_subsequence()
+    sfx = _suffix(dtype)
+    if compute_device_pool is not None:
+        return compute_device_pool.heston_sums(p, R, nT, strikes, seed, sub, sfx)
+    ctx = current_context()
+    L = _lib.lib()
+    k_arr, nK = _lib.strikes_array(strikes)
+    launch = getattr(L, f"cb_heston_price_launch_{sfx}")
+    _lib.check(launch(ctx.handle, ctypes.byref(p), R, nT, k_arr, nK, seed, sub, 0, (R + 1) // 2, None, None, None, None))
+    sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+    _lib.check(L.cb_heston_price_finish(ctx.handle, nK, sums, sumsq))
+    return list(sums), list(sumsq)
+
+
+def simulate_and_compute_option_price(
+        x0: float, v0: float, r: float, rho: float, sigma_v: float, kappa: float, v_bar: float, T: float, K: float,
+        nT: int, R: int, numerical_package_bundle: tp.Optional[tp.Type[NumericalPackageBundle]] = B200Bundle,
+        verbose: bool = False) -> float:
+    """Price a European call under Heston by Monte Carlo: the fused kernel, one launch."""
+    _require_b200(numerical_package_bundle)
+    if verbose:
+        print(f'computing on device={ComputeDeviceManager.get_current_compute_device_id()}')
+    sums, _ = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, [K])
+    return float(math.exp(-r * T) * sums[0] / int(R))
+
+
+def price_with_standard_error(x0, v0, r, rho, sigma_v, kappa, v_bar, T, K, nT, R, dtype=np.float32,
+                              compute_device_pool: tp.Optional[ComputeDevicePool] = None) -> tp.Tuple[float, float]:
+    sums, sumsq = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, [K], dtype, compute_device_pool)
+    price, se = _price_from_sums(r, T, int(R), sums, sumsq)
+    return float(price[0]), float(se[0])
+
+
+def price_strike_sweep(x0, v0, r, rho, sigma_v, kappa, v_bar, T, strikes, nT, R, dtype=np.float64,
+                       compute_device_pool: tp.Optional[ComputeDevicePool] = None):
+    """Prices and standard errors for up to 64 strikes sharing one set of paths (BASELINE config 5)."""
+    sums, sumsq = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, strikes, dtype,
+                                     compute_device_pool)
+    return _price_from_sums(r, T, int(R), sums, sumsq)
+
+
+def simulate_and_compute_option_price_gpu(
+        x0: float, v0: float, r: float, rho: float, sigma_v: float, kappa: float, v_bar: float, T: float, K: float,
+        nT: int, R: int, compute_device_pool: tp.Optional[ComputeDevicePool] = None,
+        number_of_batches: tp.Optional[int] = None, verbose: bool = False) -> float:
+    """Multi-GPU pricing (heston_utilities.py:217-270).
+
+    The reference runs ``number_of_batches`` independent simulations of ceil(R/nb)
+    paths through ``map_reduce`` and averages the batch prices, i.e. it prices with
+    nb*ceil(R/nb) paths in total.  Here that total is simulated as ONE sharded run:
+    each GPU takes a contiguous block of antithetic pairs and a single NCCL allreduce
+    combines the sums -- the same estimator up to floating-point summation order.
+    """
+    if number_of_batches is None:
+        number_of_batches = 1 if compute_device_pool is None else compute_device_pool.number_of_devices
+    if compute_device_pool is None:
+        if verbose:
+            print(f'computing {R} paths on single GPU')
+        return simulate_and_compute_option_price(x0=x0, v0=v0, r=r, rho=rho, sigma_v=sigma_v, kappa=kappa,
+                                                 v_bar=v_bar, T=T, K=K, nT=nT, R=R)
+    per_batch = math.ceil(R / number_of_batches)
+    total = per_batch * number_of_batches
+    if verbose:
+        print(f'computing {R} paths on {compute_device_pool.number_of_devices} GPUs in '
+              f'{number_of_batches} batches of {per_batch} paths')
+    sums, _ = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, total, [K],
+                                 compute_device_pool=compute_device_pool)
+    return float(math.exp(-r * T) * sums[0] / total)

@@ -1,0 +1,180 @@
+/* cocos_b200.h -- C ABI of libcocos_b200.so: the B200 (sm_100a) implementation of
+ * the Heston Monte-Carlo hot path of michaelnowotny/cocos.
+ *
+ * The reference has no FFI of its own: its seam is Python duck typing
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it
+ * stands in for (paths relative to the reference tree).  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a cb_status code otherwise; the message
+ *    is available from cb_last_error() (thread-local);
+ *  - the caller owns every buffer; the library never frees caller memory;
+ *  - "d_" pointers are device pointers on the context's device, "h_" pointers are
+ *    host pointers; plain C types only (no torch, no C++ types);
+ *  - a cb_ctx binds one device, one stream and a small workspace; calls on one
+ *    context must come from one thread at a time, different contexts are
+ *    independent;
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with
+ *    CB_ERR_CUDA.
+ */
+#ifndef COCOS_B200_H
+#define COCOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CB_API __attribute__((visibility("default")))
+#else
+#define CB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    CB_OK = 0,
+    CB_ERR_INVALID = 1,     /* bad argument (Python shim raises ValueError) */
+    CB_ERR_CUDA = 2,        /* CUDA runtime failure (RuntimeError) */
+    CB_ERR_NCCL = 3,        /* NCCL failure or libnccl not loadable (RuntimeError) */
+    CB_ERR_UNSUPPORTED = 4
+} cb_status;
+
+typedef struct cb_ctx cb_ctx;       /* one device + one stream + workspace */
+typedef struct cb_comm cb_comm;     /* one NCCL communicator rank */
+
+/* Heston model scalars: the arguments of simulate_heston_model
+ * (examples/stochastic_volatility/heston_utilities.py:24-35). */
+typedef struct {
+    double T, mu, kappa, v_bar, sigma_v, rho, x0, v0;
+} cb_heston_params;
+
+#define CB_MAX_STRIKES 64
+#define CB_UNIQUE_ID_BYTES 128
+
+/* ---- library / device management: cocos/device.py:95-205 ---------------- */
+CB_API const char *cb_last_error(void);
+CB_API const char *cb_version(void);
+CB_API int cb_device_count(int *n);                                   /* ComputeDeviceManager.get_compute_devices */
+CB_API int cb_device_name(int dev, char *buf, size_t buflen);         /* ComputeDevice.name */
+CB_API int cb_device_attributes(int dev, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+CB_API int cb_ctx_create(int dev, void *stream_or_null, cb_ctx **out); /* set_compute_device; NULL: own stream */
+CB_API int cb_ctx_destroy(cb_ctx *ctx);
+CB_API int cb_ctx_sync(cb_ctx *ctx);                                  /* cocos.device.sync (device.py:195-205) */
+CB_API int cb_ctx_device(cb_ctx *ctx, int *dev);
+CB_API void *cb_ctx_stream(cb_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream (used by bench.py) */
+CB_API int cb_timer_start(cb_ctx *ctx);
+CB_API int cb_timer_stop(cb_ctx *ctx, float *elapsed_ms);             /* synchronises the stop event */
+/* tuning knobs of the fused kernels: threads per block, blocks per SM, pairs per thread (0 = default) */
+CB_API int cb_ctx_set_launch(cb_ctx *ctx, int threads, int blocks_per_sm, int pairs_per_thread);
+
+/* caller-side memory helpers for hosts that do not bring their own allocator */
+CB_API int cb_malloc(cb_ctx *ctx, size_t bytes, void **d_ptr);
+CB_API int cb_free(cb_ctx *ctx, void *d_ptr);
+CB_API int cb_memcpy_h2d(cb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* synchronous */
+CB_API int cb_memcpy_d2h(cb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* synchronous */
+
+/* ---- random arrays: cocos/numerics/random.py:127-153 (rand, randn) -------
+ * Element order and stream layout are documented in DESIGN.md; `subsequence`
+ * separates launches drawn from one seed (the host generator hands them out). */
+CB_API int cb_philox_words(cb_ctx *ctx, uint32_t *d_out, uint64_t n_blocks, uint64_t first_index,
+                    uint32_t block, uint64_t seed, uint32_t subsequence);      /* raw 4-word blocks (KAT) */
+CB_API int cb_rand_f32(cb_ctx *ctx, float *d_out, uint64_t n, uint64_t seed, uint32_t subsequence);
+CB_API int cb_rand_f64(cb_ctx *ctx, double *d_out, uint64_t n, uint64_t seed, uint32_t subsequence);
+CB_API int cb_randn_f32(cb_ctx *ctx, float *d_out, uint64_t n, uint64_t seed, uint32_t subsequence);
+CB_API int cb_randn_f64(cb_ctx *ctx, double *d_out, uint64_t n, uint64_t seed, uint32_t subsequence);
+/* randn_antithetic / rand_antithetic (random.py:190-245): `dims[ndim]` is the OUTPUT
+ * shape (row-major), draws fill the first ceil(d/2) entries along `axis`, the
+ * remaining floor(d/2) are the reflections (-z, or 1-u). */
+CB_API int cb_randn_antithetic_f32(cb_ctx *ctx, float *d_out, const uint64_t *dims, int ndim, int axis,
+                            uint64_t seed, uint32_t subsequence);
+CB_API int cb_randn_antithetic_f64(cb_ctx *ctx, double *d_out, const uint64_t *dims, int ndim, int axis,
+                            uint64_t seed, uint32_t subsequence);
+CB_API int cb_rand_antithetic_f32(cb_ctx *ctx, float *d_out, const uint64_t *dims, int ndim, int axis,
+                           uint64_t seed, uint32_t subsequence);
+CB_API int cb_rand_antithetic_f64(cb_ctx *ctx, double *d_out, const uint64_t *dims, int ndim, int axis,
+                           uint64_t seed, uint32_t subsequence);
+
+/* ---- Heston paths ---------------------------------------------------------
+ * Parity kernels: simulate_heston_model (heston_utilities.py:58-96) with the
+ * normals injected.  d_Z is [N-1][ceil(R/2)][2]; path i < ceil(R/2) uses +Z, path
+ * i >= ceil(R/2) uses -Z[i-ceil(R/2)] (random.py:199-214).  Operation order and
+ * roundings are the reference's; d_x, d_v receive the R terminal values. */
+CB_API int cb_heston_terminal_injected_f32(cb_ctx *ctx, const float *d_Z, const cb_heston_params *p,
+                                    uint64_t R, uint32_t N, float *d_x, float *d_v);
+CB_API int cb_heston_terminal_injected_f64(cb_ctx *ctx, const double *d_Z, const cb_heston_params *p,
+                                    uint64_t R, uint32_t N, double *d_x, double *d_v);
+/* Same, taking HOST buffers: copies Z in, runs, copies x and v out (end-to-end form). */
+CB_API int cb_heston_terminal_injected_host_f32(cb_ctx *ctx, const float *h_Z, const cb_heston_params *p,
+                                         uint64_t R, uint32_t N, float *h_x, float *h_v);
+
+/* Fused kernel: in-kernel Philox + Box-Muller + antithetic pair + Euler steps +
+ * call payoff reduction = simulate_and_compute_option_price
+ * (heston_utilities.py:122-164) without materialising anything.
+ *   R, N          paths and time points of the whole simulation (N-1 Euler steps)
+ *   pair_first, pair_count   the antithetic pairs [pair_first, pair_first+pair_count)
+ *                 of the ceil(R/2) global pairs this call simulates (a shard);
+ *                 pair p owns paths p and p+ceil(R/2); the last pair of an odd R
+ *                 has no partner
+ *   h_strikes[nK] strikes sharing the same paths (1 <= nK <= CB_MAX_STRIKES)
+ *   comm          NULL, or a communicator: one ncclAllReduce(sum, double) of the
+ *                 2*nK partial sums follows the kernel on the same stream
+ *                 (replaces ComputeDevicePool.map_reduce's host fold,
+ *                 cocos/multi_processing/device_pool.py:246-251)
+ *   d_x, d_v      NULL, or device arrays receiving terminal values of this shard:
+ *                 path of pair p at [p-pair_first], partner at
+ *                 [pair_count + p-pair_first] (reference layout when the shard is
+ *                 the whole simulation)
+ *   d_traj        NULL, or [N][2*pair_count] (same path layout per row): the whole
+ *                 log-price trajectory, row 0 = x0 (path-materialising mode)
+ * _launch is asynchronous; _finish synchronises the stream and copies the sums
+ * (UNDISCOUNTED: sum of payoffs, sum of squared antithetic-unit averages) out. */
+CB_API int cb_heston_price_launch_f32(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
+                               const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                               uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                               float *d_x, float *d_v, float *d_traj);
+CB_API int cb_heston_price_launch_f64(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
+                               const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                               uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                               double *d_x, double *d_v, double *d_traj);
+CB_API int cb_heston_price_finish(cb_ctx *ctx, int nK, double *h_sum, double *h_sumsq);
+
+/* compute_option_price_from_simulated_paths (heston_utilities.py:99-119) on a
+ * device array of terminal log prices in the reference layout. */
+CB_API int cb_call_payoff_sums_f32(cb_ctx *ctx, const float *d_x, uint64_t R, const double *h_strikes, int nK,
+                            double *h_sum, double *h_sumsq);
+CB_API int cb_call_payoff_sums_f64(cb_ctx *ctx, const double *d_x, uint64_t R, const double *h_strikes, int nK,
+                            double *h_sum, double *h_sumsq);
+
+/* ---- Monte-Carlo pi: estimate_pi (examples/monte_carlo_pi/
+ * monte_carlo_pi_multi_gpu_example.py:18-33) fused: draws, test and count in one
+ * kernel.  antithetic != 0 gives the rand_antithetic([n], 0) point layout. */
+CB_API int cb_pi_count_launch(cb_ctx *ctx, uint64_t n, uint64_t seed, uint32_t subsequence, int antithetic,
+                       uint64_t draw_first, uint64_t draw_count, cb_comm *comm);
+CB_API int cb_pi_count_finish(cb_ctx *ctx, uint64_t *h_inside);
+
+/* ---- collectives: stands in for ComputeDevicePool's process pool
+ * (cocos/multi_processing/device_pool.py:58-253).  libnccl.so.2 is loaded on
+ * first use. */
+CB_API int cb_comm_unique_id(void *h_id /* CB_UNIQUE_ID_BYTES */);
+CB_API int cb_comm_init_rank(cb_ctx *ctx, int nranks, int rank, const void *h_id, cb_comm **out);
+CB_API int cb_comm_init_all(int n, cb_ctx *const *ctxs, cb_comm **out /* [n] */);   /* one process, n devices */
+CB_API int cb_comm_destroy(cb_comm *comm);
+CB_API int cb_allreduce_sum_f64(cb_ctx *ctx, cb_comm *comm, double *d_buf, size_t count);
+CB_API int cb_group_start(void);
+CB_API int cb_group_end(void);
+
+/* ---- pipe-peak calibration (roofline denominators) ---------
+ * kind: 0 FFMA, 1 MUFU.LG2, 2 MUFU.SQRT, 3 MUFU.SIN, 4 MUFU.EX2, 5 MUFU.RSQ, 6 DFMA,
+ *       7 Philox4x32-10 calls, 8 HBM write (bytes), 9 FMNMX/LOP3 (ALU pipe),
+ *       10 HBM copy (read+write bytes)
+ * ops_per_s: thread-level operations per second (FFMA counts 1 op = 2 flop). */
+CB_API int cb_peak_measure(cb_ctx *ctx, int kind, int repeats, double *ops_per_s, float *ms_best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COCOS_B200_H */
