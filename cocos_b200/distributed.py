@@ -1,0 +1,87 @@
+"""One-process-per-GPU sharding of the Heston path (``torchrun`` / ``torch.distributed`` launch).
+
+``torch.distributed`` is plumbing only: rendezvous, the broadcast of the NCCL unique
+id, barriers and the max-over-ranks of timings.  The data path has exactly one
+collective -- the ``ncclAllReduce`` of the 2*nK payoff sums that
+``cb_heston_price_launch_*`` issues on the kernel's own stream -- and every rank
+simulates a disjoint, contiguous block of antithetic pairs from a disjoint Philox
+counter range, so prices do not depend on the number of GPUs (up to fp64 summation
+order).  Stands in for the process pool of cocos/multi_processing/device_pool.py:103-128.
+"""
+import ctypes
+import math
+import os
+import typing as tp
+
+import numpy as np
+
+from . import _lib
+from .multi_processing.utilities import shard_range
+
+
+def env_rank_world() -> tp.Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from the torchrun environment (1-process defaults)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def pair_shard(R: int, world_size: int, rank: int) -> tp.Tuple[int, int]:
+    """(first, count) of the antithetic pairs rank ``rank`` simulates out of ceil(R/2)."""
+    return shard_range((int(R) + 1) // 2, world_size, rank)
+
+
+def broadcast_unique_id(group=None) -> bytes:
+    """Rank 0 creates the NCCL unique id; everybody receives it through torch.distributed."""
+    import torch.distributed as dist
+    box = [None]
+    if dist.get_rank(group) == 0:
+        buf = ctypes.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        _lib.check(_lib.lib().cb_comm_unique_id(buf))
+        box[0] = bytes(buf.raw)
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+class ShardedPricer:
+    """Rank-local handle: context on this rank's GPU plus its NCCL communicator."""
+
+    def __init__(self, device: int, rank: int, world_size: int, unique_id: tp.Optional[bytes] = None):
+        self.rank, self.world_size = rank, world_size
+        self.ctx = _lib.context(device)
+        self.comm = None
+        if world_size > 1:
+            if unique_id is None or len(unique_id) != _lib.UNIQUE_ID_BYTES:
+                raise ValueError("a 128-byte NCCL unique id is required when world_size > 1")
+            handle = ctypes.c_void_p()
+            _lib.check(_lib.lib().cb_comm_init_rank(self.ctx.handle, world_size, rank, unique_id,
+                                                    ctypes.byref(handle)))
+            self.comm = handle
+
+    def launch(self, params: "_lib.HestonParams", R: int, nT: int, strikes, seed: int, subsequence: int,
+               dtype_suffix: str = "f32"):
+        """Asynchronous: this rank's shard of the simulation, then the allreduce, on one stream."""
+        k_arr, nK = _lib.strikes_array(strikes)
+        first, count = pair_shard(R, self.world_size, self.rank)
+        fn = getattr(_lib.lib(), f"cb_heston_price_launch_{dtype_suffix}")
+        _lib.check(fn(self.ctx.handle, ctypes.byref(params), int(R), int(nT), k_arr, nK, int(seed), int(subsequence),
+                      first, count, self.comm, None, None, None))
+        return nK
+
+    def finish(self, nK: int):
+        sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+        _lib.check(_lib.lib().cb_heston_price_finish(self.ctx.handle, nK, sums, sumsq))
+        return np.array(sums), np.array(sumsq)
+
+    def price(self, x0, v0, r, rho, sigma_v, kappa, v_bar, T, K, nT, R, seed=0, subsequence=0,
+              dtype_suffix="f32") -> float:
+        """simulate_and_compute_option_price for the WHOLE job; every rank returns the same price."""
+        p = _lib.HestonParams(float(T), float(r), float(kappa), float(v_bar), float(sigma_v), float(rho),
+                              float(x0), float(v0))
+        nK = self.launch(p, R, nT, [K], seed, subsequence, dtype_suffix)
+        sums, _ = self.finish(nK)
+        return float(math.exp(-r * T) * sums[0] / int(R))
+
+    def close(self):
+        if self.comm is not None:
+            _lib.lib().cb_comm_destroy(self.comm)
+            self.comm = None

@@ -1,0 +1,71 @@
+"""The C-ABI library: it loads, exports every symbol include/cocos_b200.h declares, fails loudly
+without a GPU, and the product never routes through the oracle.  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cocos_b200.h")).read()
+    return sorted(set(re.findall(r"^CB_API\s+[\w\s\*]+?\b(cb_\w+)\s*\(", text, flags=re.M)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    assert len(names) >= 40
+    for must in ("cb_heston_price_launch_f32", "cb_heston_price_launch_f64", "cb_heston_price_finish",
+                 "cb_heston_terminal_injected_f32", "cb_heston_terminal_injected_f64", "cb_randn_antithetic_f32",
+                 "cb_rand_antithetic_f32", "cb_pi_count_launch", "cb_comm_init_rank", "cb_allreduce_sum_f64",
+                 "cb_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from cocos_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert set(_lib.PROTOTYPES) == set(declared_symbols())       # the ctypes table covers the whole header
+    exported = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    public = set(re.findall(r" T (\w+)", exported))
+    assert public == set(declared_symbols()), public ^ set(declared_symbols())
+
+
+def test_library_is_sm100a_only():
+    from cocos_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    from cocos_b200 import _lib
+    assert _lib.lib().cb_version().decode().startswith("cocos_b200")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.device_count()
+    from cocos_b200 import heston
+    from oracle.heston_numpy import REFERENCE_PARAMS
+    with pytest.raises(RuntimeError):
+        heston.simulate_and_compute_option_price(nT=11, R=100, **REFERENCE_PARAMS)
+    import cocos_b200.numerics as cn
+    with pytest.raises(RuntimeError):
+        cn.random.randn(10)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cocos_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text, f

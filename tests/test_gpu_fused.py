@@ -1,0 +1,203 @@
+"""Fused kernel (in-kernel Philox + Box-Muller + Euler + payoff reduction) against the oracle.
+
+(a) per path, against the oracle's model of the SAME stream (Philox bits -> float64 Box-Muller -> the
+    reference update in float32/float64): tight tolerance, far below Monte-Carlo noise;
+(b) correctness check (2) of the north_star: prices within 3 standard errors of the reference's own
+    prices (tests/golden/reference_values.json "statistical", made from the unmodified reference);
+(c) size-independent properties at BASELINE sizes: shards add up, geometry does not change a path,
+    launches are reproducible.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from gpu_util import fused
+
+pytestmark = pytest.mark.gpu
+
+STRIKES64 = [0.70 + 0.60 * i / 63 for i in range(64)]
+
+
+@pytest.fixture(scope="module")
+def ctx(gpu_device):
+    c = gpu_device.current_context()
+    yield c
+    c.set_launch(0, 0, 0)
+
+
+@pytest.fixture(scope="module")
+def P(ref_params):
+    q = ref_params
+    return dict(T=q["T"], mu=q["r"], kappa=q["kappa"], v_bar=q["v_bar"], sigma_v=q["sigma_v"], rho=q["rho"],
+                x0=q["x0"], v0=q["v0"])
+
+
+def model(P, R, N, seed, sub, dtype, pair_offset=0):
+    from oracle import heston_numpy as hn
+    return hn.fused_model(P["x0"], P["v0"], P["mu"], P["rho"], P["sigma_v"], P["kappa"], P["v_bar"], P["T"], N, R,
+                          seed, sub, pair_offset=pair_offset, dtype=dtype)
+
+
+@pytest.mark.parametrize("R,N", [(20_001, 64), (4096, 101), (1, 2), (2, 3), (7, 6), (1025, 17)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_paths_match_stream_model(ctx, P, R, N, dtype):
+    from oracle import heston_numpy as hn
+    sums, sumsq, x, v = fused(ctx, P, R, N, [0.95], seed=99, sub=3, dtype=dtype, outputs=True)
+    xm, vm = model(P, R, N, 99, 3, dtype)
+    # float32 Box-Muller on MUFU vs float64: ~1e-6 per normal, accumulated over N-1 steps
+    tol = 2e-5 if N <= 101 else 1e-4
+    np.testing.assert_allclose(x[:R], xm, rtol=0, atol=tol)
+    np.testing.assert_allclose(v[:R], vm, rtol=5e-3, atol=5e-6)
+    ws, wq = hn.payoff_sums(xm, [0.95])
+    assert sums[0] == pytest.approx(ws[0], rel=1e-4, abs=1e-4)
+    assert sumsq[0] == pytest.approx(wq[0], rel=2e-4, abs=1e-4)
+    # the kernel's own sums agree with its own terminal values
+    os_, oq = hn.payoff_sums(x[:R], [0.95])
+    assert sums[0] == pytest.approx(os_[0], rel=1e-5, abs=1e-6)
+    assert sumsq[0] == pytest.approx(oq[0], rel=1e-5, abs=1e-6)
+
+
+def test_antithetic_partners(ctx, P):
+    """One Euler step: partners see -z, so x1 + x2 = 2*(x0 + (mu - v0/2) dt) up to rounding."""
+    R = 10_000
+    _, _, x, v = fused(ctx, P, R, 2, [0.95], seed=1, sub=0, outputs=True)
+    H = R // 2
+    np.testing.assert_allclose(x[:H] + x[H:R], 2 * (P["x0"] + (P["mu"] - 0.5 * P["v0"]) * P["T"]), atol=2e-6)
+    assert np.std(x[:H] - x[H:R]) > 0.05
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_multi_strike_equals_single_strike(ctx, P, dtype):
+    R, N = 50_001, 33
+    s64, q64 = fused(ctx, P, R, N, STRIKES64, seed=5, sub=1, dtype=dtype)
+    for k in (0, 17, 31, 32, 63):
+        s1, q1 = fused(ctx, P, R, N, [STRIKES64[k]], seed=5, sub=1, dtype=dtype)
+        assert s64[k] == pytest.approx(s1[0], rel=1e-9)
+        assert q64[k] == pytest.approx(q1[0], rel=1e-9)
+    s3, _ = fused(ctx, P, R, N, STRIKES64[:3], seed=5, sub=1, dtype=dtype)
+    np.testing.assert_allclose(s3, s64[:3], rtol=1e-9)
+    assert np.all(np.diff(s64) < 0)                       # call payoffs decrease in the strike
+
+
+@pytest.mark.parametrize("threads,bps,ppt", [(128, 0, 1), (128, 0, 2), (256, 0, 4), (64, 3, 2), (256, 1, 1)])
+def test_geometry_does_not_change_paths(ctx, P, threads, bps, ppt):
+    R, N = 30_003, 21
+    ctx.set_launch(0, 0, 0)
+    s0, q0, x0, v0 = fused(ctx, P, R, N, [0.95], seed=8, sub=2, outputs=True)
+    ctx.set_launch(threads, bps, ppt)
+    s1, q1, x1, v1 = fused(ctx, P, R, N, [0.95], seed=8, sub=2, outputs=True)
+    ctx.set_launch(0, 0, 0)
+    assert np.array_equal(x0[:R], x1[:R]) and np.array_equal(v0[:R], v1[:R])     # per-path bits identical
+    assert s1[0] == pytest.approx(s0[0], rel=1e-12) and q1[0] == pytest.approx(q0[0], rel=1e-12)
+
+
+def test_reproducible_and_stream_separation(ctx, P):
+    a = fused(ctx, P, 100_000, 51, [0.95], seed=3, sub=7)
+    b = fused(ctx, P, 100_000, 51, [0.95], seed=3, sub=7)
+    assert a[0][0] == b[0][0] and a[1][0] == b[1][0]       # fixed-order reduction: identical bits
+    c = fused(ctx, P, 100_000, 51, [0.95], seed=3, sub=8)
+    d = fused(ctx, P, 100_000, 51, [0.95], seed=4, sub=7)
+    assert c[0][0] != a[0][0] and d[0][0] != a[0][0]
+
+
+@pytest.mark.parametrize("R,parts", [(100_001, 2), (100_000, 8), (999, 4), (5, 8)])
+def test_shards_add_up(ctx, P, R, parts):
+    """Device-count invariance: disjoint pair ranges reproduce the whole simulation path by path."""
+    from cocos_b200.multi_processing.utilities import shard_range
+    N = 25
+    H, F = (R + 1) // 2, R // 2
+    s, q, x, v = fused(ctx, P, R, N, STRIKES64[:5], seed=21, sub=4, outputs=True)
+    tot_s, tot_q = np.zeros(5), np.zeros(5)
+    for g in range(parts):
+        first, count = shard_range(H, parts, g)
+        out = fused(ctx, P, R, N, STRIKES64[:5], seed=21, sub=4, first=first, count=count, outputs=count > 0)
+        tot_s += out[0]
+        tot_q += out[1]
+        if count:
+            xs = out[2]
+            assert np.array_equal(xs[:count], x[first:first + count])
+            n_partner = max(0, min(first + count, F) - first)
+            assert np.array_equal(xs[count:count + n_partner], x[H + first:H + first + n_partner])
+    np.testing.assert_allclose(tot_s, s, rtol=1e-12)
+    np.testing.assert_allclose(tot_q, q, rtol=1e-12)
+
+
+def test_trajectory_mode(ctx, P):
+    R, N = 8_000, 41
+    s, q, x, v, traj = fused(ctx, P, R, N, [0.95], seed=6, sub=0, outputs=True, traj=True)
+    H = R // 2
+    assert traj.shape == (N, R)
+    assert np.all(traj[0] == np.float32(P["x0"]))
+    assert np.array_equal(traj[-1], x[:R])                 # last row is the terminal value
+    s2, q2, x2, v2 = fused(ctx, P, R, N, [0.95], seed=6, sub=0, outputs=True)
+    assert np.array_equal(x2[:R], x[:R])                   # same paths as the non-materialising kernel
+    incr = np.diff(traj.astype(np.float64), axis=0)
+    assert 0.5 * math.sqrt(P["v_bar"] / (N - 1)) < incr.std() < 3 * math.sqrt(P["v0"] / (N - 1))
+    # ragged: odd R, pair count not a multiple of 4 -> scalar-store path
+    R = 4_999
+    out = fused(ctx, P, R, 9, [0.95], seed=6, sub=1, outputs=True, traj=True)
+    xr, tr = out[2], out[4]
+    assert np.array_equal(tr[-1][:R], xr[:R])
+
+
+@pytest.mark.parametrize("nT,R", [(101, 4_000_000), (253, 2_000_000), (501, 2_000_000), (1001, 1_000_000)])
+def test_price_within_3se_of_reference(gpu_device, golden_values, ref_params, nT, R):
+    """Correctness check (2): in-kernel RNG price vs the reference's NumPy price, 3 combined SE."""
+    from cocos_b200 import heston
+    from cocos_b200.numerics import random as rnd
+    rnd.seed(20261019)
+    price, se = heston.price_with_standard_error(nT=nT, R=R, **ref_params)
+    ref = golden_values["statistical"][f"nT{nT}"]
+    assert 0.3 * ref["se"] * math.sqrt(ref["paths"] / R) < se < 3 * ref["se"] * math.sqrt(ref["paths"] / R)
+    assert abs(price - ref["price"]) <= 3 * math.hypot(se, ref["se"]), (price, se, ref["price"], ref["se"])
+    plain = heston.simulate_and_compute_option_price(nT=nT, R=R, **ref_params)
+    assert abs(plain - ref["price"]) <= 3 * math.hypot(se, ref["se"])
+
+
+def test_strike_sweep_f64_within_3se(gpu_device, golden_values, ref_params):
+    """BASELINE config C5 shape: float64 state, 64 strikes sharing paths, nT = 253."""
+    from cocos_b200 import heston
+    from cocos_b200.numerics import random as rnd
+    rnd.seed(5)
+    kw = {k: ref_params[k] for k in ("x0", "v0", "r", "rho", "sigma_v", "kappa", "v_bar", "T")}
+    prices, ses = heston.price_strike_sweep(strikes=golden_values["statistical"]["strikes"], nT=253, R=2_000_000,
+                                            dtype=np.float64, **kw)
+    ref = np.array(golden_values["statistical"]["nT253"]["sweep"])
+    ref_se = golden_values["statistical"]["nT253"]["se"]
+    assert prices.shape == (64,)
+    assert np.all(np.abs(prices - ref) <= 3 * np.hypot(ses, 2.0 * ref_se) + 1e-7)
+    rnd.seed(5)
+    p32, _ = heston.price_strike_sweep(strikes=golden_values["statistical"]["strikes"], nT=253, R=2_000_000,
+                                       dtype=np.float32, **kw)
+    np.testing.assert_allclose(p32, prices, rtol=0, atol=5e-5)        # same stream, float32 vs float64 state
+
+
+def test_full_size_c3_properties(ctx, P, golden_values, ref_params):
+    """BASELINE config C3 (10M paths x 500 steps): halves add up; price within 3 SE of the reference."""
+    R, N = 10_000_000, 501
+    H = R // 2
+    whole = fused(ctx, P, R, N, [0.95], seed=0, sub=0)
+    a = fused(ctx, P, R, N, [0.95], seed=0, sub=0, first=0, count=H // 2)
+    b = fused(ctx, P, R, N, [0.95], seed=0, sub=0, first=H // 2, count=H - H // 2)
+    assert a[0][0] + b[0][0] == pytest.approx(whole[0][0], rel=1e-12)
+    assert a[1][0] + b[1][0] == pytest.approx(whole[1][0], rel=1e-12)
+    from cocos_b200.heston import _price_from_sums
+    price, se = _price_from_sums(ref_params["r"], ref_params["T"], R, whole[0], whole[1])
+    ref = golden_values["statistical"]["nT501"]
+    assert abs(price[0] - ref["price"]) <= 3 * math.hypot(se[0], ref["se"])
+
+
+def test_argument_errors(ctx, P):
+    with pytest.raises(ValueError):
+        fused(ctx, P, 100, 1, [0.95], 0, 0)                       # N < 2
+    with pytest.raises(ValueError):
+        fused(ctx, P, 0, 10, [0.95], 0, 0)                        # R < 1
+    with pytest.raises(ValueError):
+        fused(ctx, P, 100, 10, [0.95], 0, 0, first=40, count=20)  # pair range outside [0, 50)
+    with pytest.raises(ValueError):
+        fused(ctx, P, 100, 10, [1.0] * 65, 0, 0)
+    from cocos_b200 import heston
+    from oracle import heston_numpy as hn
+    with pytest.raises(TypeError):
+        heston.simulate_and_compute_option_price(nT=10, R=10, numerical_package_bundle=object, **hn.REFERENCE_PARAMS)
