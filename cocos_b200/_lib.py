@@ -41,6 +41,7 @@ PROTOTYPES = {
     "cb_timer_start": (c_int, [c_void_p]),
     "cb_timer_stop": (c_int, [c_void_p, P(c_float)]),
     "cb_ctx_set_launch": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "cb_ctx_set_variant": (c_int, [c_void_p, c_int]),
     "cb_malloc": (c_int, [c_void_p, c_size, P(c_void_p)]),
     "cb_free": (c_int, [c_void_p, c_void_p]),
     "cb_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size]),
@@ -142,6 +143,9 @@ class Context:
 
     def set_launch(self, threads=0, blocks_per_sm=0, pairs_per_thread=0):
         check(lib().cb_ctx_set_launch(self.handle, threads, blocks_per_sm, pairs_per_thread))
+
+    def set_variant(self, variant=0):
+        check(lib().cb_ctx_set_variant(self.handle, variant))
 
     def timer_start(self):
         check(lib().cb_timer_start(self.handle))

@@ -56,7 +56,8 @@ struct cb_ctx {
     void *scratch = nullptr;                 // grow-only staging buffer for the *_host entry points
     size_t scratch_bytes = 0;
     int threads = 0, blocks_per_sm = 0, ppt = 0;   // 0 = default
-    std::map<std::tuple<int, int, int, int>, std::pair<int, int>> occ_cache;   // (is64, ppt, multi, threads) -> (bps, regs)
+    int variant = 0;
+    std::map<std::tuple<int, int, int, int, int>, std::pair<int, int>> occ_cache;   // (is64, ppt, multi, threads, variant) -> (bps, regs)
 };
 
 struct cb_comm {
@@ -179,12 +180,19 @@ extern "C" CB_API int cb_timer_stop(cb_ctx *c, float *elapsed_ms) {
 extern "C" CB_API int cb_ctx_set_launch(cb_ctx *c, int threads, int blocks_per_sm, int pairs_per_thread) {
     CB_REQUIRE(c != nullptr, "context is NULL");
     CB_REQUIRE(threads == 0 || (threads >= 32 && threads <= 256 && threads % 32 == 0), "threads must be 0 or a multiple of 32 in [32,256]");
-    CB_REQUIRE(blocks_per_sm >= 0 && blocks_per_sm <= 32, "blocks_per_sm must be in [0,32]");
+    CB_REQUIRE(blocks_per_sm >= 0 && blocks_per_sm <= 64, "blocks_per_sm must be in [0,64]");
     CB_REQUIRE(pairs_per_thread == 0 || pairs_per_thread == 1 || pairs_per_thread == 2 || pairs_per_thread == 4,
                "pairs_per_thread must be 0, 1, 2 or 4");
     c->threads = threads;
     c->blocks_per_sm = blocks_per_sm;
     c->ppt = pairs_per_thread;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_ctx_set_variant(cb_ctx *c, int variant) {
+    CB_REQUIRE(c != nullptr, "context is NULL");
+    CB_REQUIRE(variant >= 0 && variant <= 3, "variant must be in [0,3]");
+    c->variant = variant;
     return CB_OK;
 }
 
@@ -544,24 +552,25 @@ template <typename real>
 static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, LaunchShape *s) {
     const int threads = c->threads ? c->threads : 128;
     const int ppt = traj ? 4 : (c->ppt ? c->ppt : 1);
-    const auto key = std::make_tuple((int)(sizeof(real) == 8), traj ? -4 : ppt, (int)multi, threads);
+    const int variant = (sizeof(real) == 4 && !multi && !traj) ? c->variant : 0;
+    const auto key = std::make_tuple((int)(sizeof(real) == 8), traj ? -4 : ppt, (int)multi, threads, variant);
     auto it = c->occ_cache.find(key);
     if (it == c->occ_cache.end()) {
         int bps = 0, regs = 0;
-        CB_CUDA((fused_occupancy<real>(threads, traj ? -4 : ppt, multi, &bps, &regs)));
+        CB_CUDA((fused_occupancy<real>(threads, traj ? -4 : ppt, multi, variant, &bps, &regs)));
         it = c->occ_cache.emplace(key, std::make_pair(bps, regs)).first;
     }
     int bps = it->second.first;
     CB_REQUIRE(bps >= 1, "fused kernel does not fit on an SM with %d threads", threads);
-    if (c->blocks_per_sm > 0) bps = std::min(bps, c->blocks_per_sm);
     const uint64_t per_block = (uint64_t)threads * ppt;
     const uint64_t items = std::max<uint64_t>(1, (pair_count + per_block - 1) / per_block);
     const uint64_t resident = (uint64_t)c->sm_count * bps;
     uint64_t blocks;
-    if (items <= resident) {
+    if (c->blocks_per_sm > 0) {
+        // explicit grid: sm_count * blocks_per_sm blocks (more than fit at once => the hardware back-fills)
+        blocks = std::min<uint64_t>(items, (uint64_t)c->sm_count * c->blocks_per_sm);
+    } else if (items <= resident) {
         blocks = items;
-    } else if (c->blocks_per_sm > 0) {
-        blocks = resident;
     } else {
         double best = -1.0;
         blocks = resident;
@@ -580,6 +589,7 @@ static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, L
     s->threads = threads;
     s->blocks = (int)blocks;
     s->pairs_per_thread = ppt;
+    s->variant = variant;
     return CB_OK;
 }
 
@@ -697,7 +707,7 @@ extern "C" CB_API int cb_pi_count_finish(cb_ctx *c, uint64_t *h_inside) {
 extern "C" CB_API int cb_peak_measure(cb_ctx *c, int kind, int repeats, double *ops_per_s, float *ms_best) {
     CB_CTX(c);
     CB_REQUIRE(ops_per_s != nullptr, "ops_per_s is NULL");
-    CB_REQUIRE(kind >= 0 && kind <= 10, "kind must be in [0,10]");
+    CB_REQUIRE(kind >= 0 && kind <= 17, "kind must be in [0,17]");
     if (repeats < 1) repeats = 1;
     size_t bytes = 4096;
     if (kind == 8 || kind == 10) bytes = (size_t)4 << 30;   // far larger than the 126 MB L2

@@ -10,8 +10,8 @@
 // One thread owns PPT antithetic pairs (path p and its partner p+ceil(R/2), which
 // sees the negated normals) for all N-1 steps.  Nothing is read from or written to
 // HBM inside the time loop unless the trajectory is requested.  Per pair-step:
-// 6 MUFU (lg2, sqrt, sin, cos, 2x sqrt(v)) against ~41 other issue slots, so the
-// kernel is bound by the MUFU pipe with the issue port close behind.
+// 5 MUFU (lg2, sin, cos, 2x sqrt(v*r^2)) against ~43 other issue slots: the MUFU (XU)
+// pipe and the issue port are both close to their limits.
 //
 // Algebra (statistical mode, not the parity order): with a = 1-kappa*dt,
 // b = kappa*v_bar*dt, w = sigma_v*(rho*dB0 + sqrt(1-rho^2)*dB1):
@@ -41,14 +41,46 @@ struct StepRegs {
           floor_v(c.floor_v), neg2ln2_dt(c.neg2ln2_dt), two_pi(pin(kTwoPi)) {}
 };
 
+// The draws of one Euler step: two floats in [1,2) built from random mantissa bits (no I2F: it shares the XU pipe).
+struct StepDraw {
+    float t_radius;   // 23 random bits: U = 2 - t_radius in (0,1]
+    float t_angle;    // 19 random bits: theta = 2 pi t_angle - 3 pi
+};
+
+// One Philox4x32-10 block (128 bits) feeds THREE Euler steps (126 bits used): the 32x32->64 multiplies of Philox
+// (IMAD.WIDE: 4 issue cycles each on the FMA pipe, not overlappable with FP32 work) are the most expensive
+// non-MUFU instructions of the loop, so the block is used to the last bit.
+//   step j (j = 0,1,2): radius <- w_j[31:9];  angle <- w_j[8:0] : w3[31-10j : 22-10j]
+__device__ __forceinline__ void split_draws(const uint4 &o, StepDraw &d0, StepDraw &d1, StepDraw &d2) {
+    constexpr uint32_t kMask = 0x007FFFF0u, kOne = 0x3F800000u;
+    d0.t_radius = mantissa_float(o.x);
+    d1.t_radius = mantissa_float(o.y);
+    d2.t_radius = mantissa_float(o.z);
+    // funnel shift: upper word of (w_j : w3 << 10j) << 14 has w_j[8:0] : w3 bits in its low 23 bits
+    d0.t_angle = __uint_as_float((__funnelshift_l(o.w, o.x, 14) & kMask) | kOne);
+    d1.t_angle = __uint_as_float((__funnelshift_l(o.w << 10, o.y, 14) & kMask) | kOne);
+    d2.t_angle = __uint_as_float((__funnelshift_l(o.w << 20, o.z, 14) & kMask) | kOne);
+}
+
+// One Euler step of an antithetic pair from one (radius, angle) word pair.
+//
+// With r^2 = -2 dt ln U and (c, s) = (cos, sin)(theta) the reference needs sqrt(v)*dB0 = sqrt(v)*r*c and
+// sqrt(v)*(rho dB0 + rho' dB1) = sqrt(v)*r*(rho c + rho' s).  Since sqrt(v)*r = sqrt(v*r^2), the radius never has to
+// be formed: q = MUFU.SQRT(v * r^2) replaces MUFU.SQRT(r^2) and MUFU.SQRT(v) -- 5 MUFU per pair-step instead of 6,
+// at the same count of FP32 instructions.
 template <typename real>
-__device__ __forceinline__ void euler_pair(real &x1, real &v1, real &x2, real &v2, real b0, real w,
+__device__ __forceinline__ void euler_pair(real &x1, real &v1, real &x2, real &v2, float t_radius, float t_angle,
                                            const StepRegs<real> &k) {
-    const real s1 = root(v1), s2 = root(v2);
-    x1 = fma(s1, b0, fma(v1, k.drift_v, x1));
-    x2 = fma(s2, -b0, fma(v2, k.drift_v, x2));
-    v1 = fmax(fma(s1, w, fma(v1, k.decay, k.pull)), k.floor_v);
-    v2 = fmax(fma(s2, -w, fma(v2, k.decay, k.pull)), k.floor_v);
+    const float U = 2.0f - t_radius;                                      // (0,1]
+    const float r2 = mufu_lg2(U) * k.neg2ln2_dt;                          // (r*sqrt(dt))^2 >= 0
+    const float theta = fmaf(t_angle, k.two_pi, -kThreePi);               // [-pi,pi)
+    const real cs = (real)mufu_cos(theta), sn = (real)mufu_sin(theta);
+    const real g = fma(cs, k.w0, sn * k.w1);                              // sigma_v*(rho c + rho' s)
+    const real q1 = root(v1 * (real)r2), q2 = root(v2 * (real)r2);        // sqrt(v)*r*sqrt(dt)
+    x1 = fma(q1, cs, fma(v1, k.drift_v, x1));
+    x2 = fma(q2, -cs, fma(v2, k.drift_v, x2));
+    v1 = fmax(fma(q1, g, fma(v1, k.decay, k.pull)), k.floor_v);
+    v2 = fmax(fma(q2, -g, fma(v2, k.decay, k.pull)), k.floor_v);
 }
 
 template <int N>
@@ -66,8 +98,8 @@ struct PairStore<4> {
 
 // ---- the kernel -------------------------------------------------------------
 
-template <typename real, int PPT, bool MULTI, bool TRAJ>
-__global__ void __launch_bounds__(kMaxThreads)
+template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1, int ROUNDS = 10>
+__global__ void __launch_bounds__(kMaxThreads, MINB)
 heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace ws,
                     real *__restrict__ x_out, real *__restrict__ v_out, real *__restrict__ traj) {
     static_assert(!TRAJ || PPT == 4, "trajectory mode stores 4 consecutive pairs per thread");
@@ -76,7 +108,6 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
     const uint64_t per_iter = total * PPT;
     const uint64_t iters = (c.pair_count + per_iter - 1) / per_iter;   // same for every thread: warps stay converged
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t blocks2 = c.steps >> 1;
     const uint64_t row_len = 2 * c.pair_count;
     const bool vec_ok = TRAJ && (c.pair_count % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(traj) & (4 * sizeof(real) - 1)) == 0);
@@ -119,14 +150,10 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
         }
 
         // one Euler step for every pair of this thread from one (radius, angle) word pair each
-        auto advance = [&](const uint32_t (&o_r)[PPT], const uint32_t (&o_a)[PPT], uint32_t step_no) {
+        auto advance = [&](const StepDraw (&d)[PPT], uint32_t step_no) {
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
-                float z0, z1;
-                box_muller(o_r[q], o_a[q], k.neg2ln2_dt, k.two_pi, z0, z1);      // already scaled by sqrt(dt)
-                const real b0 = (real)z0, b1 = (real)z1;
-                const real w = fma(b0, k.w0, b1 * k.w1);
-                euler_pair(x1[q], v1[q], x2[q], v2[q], b0, w, k);
+                euler_pair(x1[q], v1[q], x2[q], v2[q], d[q].t_radius, d[q].t_angle, k);
             }
             if constexpr (TRAJ) {
                 const real shift = c.x0 + (real)step_no * c.mu_dt;
@@ -152,25 +179,46 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             }
         };
 
-#pragma unroll 2
-        for (uint32_t b = 0; b < blocks2; ++b) {
-            uint32_t r0[PPT], a0[PPT], r1[PPT], a1[PPT];
+        // Three Euler steps per Philox call (split_draws): ceil(steps/3) calls per pair.
+        const uint32_t calls = c.steps / 3, rest = c.steps - 3 * calls;
+        if constexpr (PIPE) {
+            // software pipeline: the Philox call of block b+1 (a 10-round dependent integer chain) is issued
+            // next to the MUFU-heavy Box-Muller/Euler work of block b, so every warp feeds the XU queue and the
+            // integer pipes at the same time instead of alternating between the two phases
+            uint4 cur[PPT];
 #pragma unroll
-            for (int q = 0; q < PPT; ++q) {
-                const uint4 o = rng[q].block(b, keys);
-                r0[q] = o.x; a0[q] = o.y; r1[q] = o.z; a1[q] = o.w;
-            }
-            advance(r0, a0, 2 * b + 1);
-            advance(r1, a1, 2 * b + 2);
-        }
-        if (c.steps & 1u) {
-            uint32_t r0[PPT], a0[PPT];
+            for (int q = 0; q < PPT; ++q) cur[q] = rng[q].template block<ROUNDS>(0u, keys);
+            for (uint32_t b = 0; b < calls; ++b) {
+                uint4 nxt[PPT];
+                StepDraw d0[PPT], d1[PPT], d2[PPT];
 #pragma unroll
-            for (int q = 0; q < PPT; ++q) {
-                const uint4 o = rng[q].block(blocks2, keys);
-                r0[q] = o.x; a0[q] = o.y;
+                for (int q = 0; q < PPT; ++q) {
+                    nxt[q] = rng[q].template block<ROUNDS>(b + 1, keys);
+                    split_draws(cur[q], d0[q], d1[q], d2[q]);
+                }
+                advance(d0, 3 * b + 1);
+                advance(d1, 3 * b + 2);
+                advance(d2, 3 * b + 3);
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) cur[q] = nxt[q];
             }
-            advance(r0, a0, c.steps);
+            if (rest) {
+                StepDraw d0[PPT], d1[PPT], d2[PPT];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) split_draws(cur[q], d0[q], d1[q], d2[q]);
+                advance(d0, 3 * calls + 1);
+                if (rest > 1) advance(d1, 3 * calls + 2);
+            }
+        } else {
+            for (uint32_t b = 0; b < calls + (rest ? 1u : 0u); ++b) {
+                StepDraw d0[PPT], d1[PPT], d2[PPT];
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) split_draws(rng[q].template block<ROUNDS>(b, keys), d0[q], d1[q], d2[q]);
+                const uint32_t left = c.steps - 3 * b;
+                advance(d0, 3 * b + 1);
+                if (left > 1) advance(d1, 3 * b + 2);
+                if (left > 2) advance(d2, 3 * b + 3);
+            }
         }
 
         // ---- terminal values and payoffs ----
@@ -277,11 +325,25 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 
 // ---- host side ---------------------------------------------------------------
 
-template <typename real, int PPT, bool MULTI, bool TRAJ>
+template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1>
 static cudaError_t launch_one(const FusedConsts<real> &c, const LaunchShape &s, ReduceWorkspace ws,
                               real *d_x, real *d_v, real *d_traj, cudaStream_t stream) {
-    heston_fused_kernel<real, PPT, MULTI, TRAJ><<<s.blocks, s.threads, 0, stream>>>(c, ws, d_x, d_v, d_traj);
+    heston_fused_kernel<real, PPT, MULTI, TRAJ, PIPE, MINB><<<s.blocks, s.threads, 0, stream>>>(c, ws, d_x, d_v, d_traj);
     return cudaGetLastError();
+}
+
+// experimental variants of the float single-strike kernel (variant = 1..3), selected by cb_ctx_set_variant
+template <int PPT>
+static const void *variant_fn(int variant) {
+    switch (variant) {
+        case 1: return (const void *)heston_fused_kernel<float, PPT, false, false, false, 1>;          // not software-pipelined
+        case 2: return (const void *)heston_fused_kernel<float, PPT, false, false, true, (PPT == 4 ? 2 : 4)>;
+        case 3: return (const void *)heston_fused_kernel<float, PPT, false, false, true, 1, 6>;   // timing experiment only: 6 Philox rounds
+        default: return (const void *)heston_fused_kernel<float, PPT, false, false, true, 1>;
+    }
+}
+static const void *variant_fn(int ppt, int variant) {
+    return ppt == 1 ? variant_fn<1>(variant) : ppt == 2 ? variant_fn<2>(variant) : variant_fn<4>(variant);
 }
 
 template <typename real>
@@ -289,6 +351,13 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
                                 real *d_x, real *d_v, real *d_traj, cudaStream_t stream) {
     const bool multi = c.nK > 1;
     if (d_traj != nullptr) return launch_one<real, 4, true, true>(c, s, ws, d_x, d_v, d_traj, stream);
+    if constexpr (sizeof(real) == 4) {
+        if (!multi && s.variant > 0) {
+            void *args[] = {(void *)&c, (void *)&ws, (void *)&d_x, (void *)&d_v, (void *)&d_traj};
+            return cudaLaunchKernel(variant_fn(s.pairs_per_thread, s.variant), dim3(s.blocks), dim3(s.threads), args, 0,
+                                    stream);
+        }
+    }
     switch (s.pairs_per_thread) {
         case 1:
             return multi ? launch_one<real, 1, true, false>(c, s, ws, d_x, d_v, nullptr, stream)
@@ -305,8 +374,16 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
 }
 
 template <typename real>
-cudaError_t fused_occupancy(int threads, int ppt, bool multi, int *blocks_per_sm, int *regs) {
+cudaError_t fused_occupancy(int threads, int ppt, bool multi, int variant, int *blocks_per_sm, int *regs) {
     const void *fn = nullptr;
+    if (sizeof(real) == 4 && !multi && variant > 0 && ppt > 0) {
+        fn = variant_fn(ppt, variant);
+        cudaFuncAttributes a;
+        cudaError_t e0 = cudaFuncGetAttributes(&a, fn);
+        if (e0 != cudaSuccess) return e0;
+        if (regs) *regs = a.numRegs;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
+    }
     if (ppt == 1) fn = multi ? (const void *)heston_fused_kernel<real, 1, true, false> : (const void *)heston_fused_kernel<real, 1, false, false>;
     else if (ppt == 2) fn = multi ? (const void *)heston_fused_kernel<real, 2, true, false> : (const void *)heston_fused_kernel<real, 2, false, false>;
     else if (ppt == 4) fn = multi ? (const void *)heston_fused_kernel<real, 4, true, false> : (const void *)heston_fused_kernel<real, 4, false, false>;
@@ -323,7 +400,7 @@ template cudaError_t launch_heston_fused<float>(const FusedConsts<float> &, cons
                                                 float *, float *, float *, cudaStream_t);
 template cudaError_t launch_heston_fused<double>(const FusedConsts<double> &, const LaunchShape &, ReduceWorkspace,
                                                  double *, double *, double *, cudaStream_t);
-template cudaError_t fused_occupancy<float>(int, int, bool, int *, int *);
-template cudaError_t fused_occupancy<double>(int, int, bool, int *, int *);
+template cudaError_t fused_occupancy<float>(int, int, bool, int, int *, int *);
+template cudaError_t fused_occupancy<double>(int, int, bool, int, int *, int *);
 
 }  // namespace cb

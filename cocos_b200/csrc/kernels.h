@@ -17,6 +17,7 @@ struct LaunchShape {
     int threads;            // per block
     int blocks;             // grid
     int pairs_per_thread;   // 1, 2 or 4 interleaved pairs per thread
+    int variant;            // 0 = default kernel; >0 = experimental variants of the float single-strike kernel
 };
 
 // Launch-uniform constants of the fused kernels, precomputed in double on the host.
@@ -52,7 +53,7 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
                                 real *d_x, real *d_v, real *d_traj, cudaStream_t stream);
 
 template <typename real>
-cudaError_t fused_occupancy(int threads, int pairs_per_thread, bool multi, int *blocks_per_sm, int *regs);
+cudaError_t fused_occupancy(int threads, int pairs_per_thread, bool multi, int variant, int *blocks_per_sm, int *regs);
 
 // parity kernels (reference operation order, injected normals)
 struct InjectedConsts32 {

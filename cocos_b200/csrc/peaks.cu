@@ -86,6 +86,54 @@ peak_alu_kernel(uint32_t *out, uint32_t a, uint32_t b) {
     if (s == 0x12345678u) out[0] = s;
 }
 
+// Integer-multiply experiments (what does Philox's 32x32->64 product cost next to other work?)
+//   MODE 0: IMAD.WIDE.U32 only            MODE 1: IMAD.HI.U32 + IMAD (lo) pairs
+//   MODE 2: IMAD.WIDE + 4 independent FFMA  MODE 3: IMAD.HI only   MODE 4: IMAD lo only
+//   MODE 5: IMAD.WIDE + 4 independent LOP3  MODE 6: IMAD.HI+IMAD.LO + 4 FFMA
+template <int MODE>
+__global__ void __launch_bounds__(256)
+peak_imad_kernel(uint32_t *out, uint32_t m0, float fa, float fb) {
+    uint32_t x[kChains];
+    float f[4];
+    uint32_t l[4];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) x[i] = threadIdx.x * 2654435761u + i;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[i] = 1.0f + i; l[i] = threadIdx.x + i; }
+#pragma unroll 1
+    for (int it = 0; it < kIters; it += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) {
+                if constexpr (MODE == 0 || MODE == 2 || MODE == 5) {
+                    const uint64_t p = (uint64_t)x[i] * m0;
+                    x[i] = (uint32_t)(p >> 32) ^ (uint32_t)p;
+                } else if constexpr (MODE == 1 || MODE == 6) {
+                    x[i] = __umulhi(x[i], m0) ^ (x[i] * m0);
+                } else if constexpr (MODE == 3) {
+                    x[i] = __umulhi(x[i], m0);
+                } else {
+                    x[i] = x[i] * m0 + 1u;
+                }
+                if constexpr (MODE == 2 || MODE == 6) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) f[j] = fmaf(f[j], fa, fb);
+                }
+                if constexpr (MODE == 5) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) l[j] = (l[j] | m0) ^ l[(j + 1) & 3];
+                }
+            }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) s ^= x[i];
+    float t = f[0] + f[1] + f[2] + f[3];
+    s ^= l[0] ^ l[1] ^ l[2] ^ l[3];
+    if (s == 0x12345678u || t == 123.456f) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256)
 peak_hbm_write_kernel(float4 *out, size_t n_vec) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -133,6 +181,13 @@ cudaError_t launch_peak_kernel(int kind, int sm_count, void *d_scratch, size_t s
             *work_done = (double)n_vec * 32.0;
             break;
         }
+        case 11: peak_imad_kernel<0><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 12: peak_imad_kernel<1><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 13: peak_imad_kernel<2><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 14: peak_imad_kernel<3><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 15: peak_imad_kernel<4><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 16: peak_imad_kernel<5><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 17: peak_imad_kernel<6><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -80,6 +80,7 @@ struct PairStream {
         p1lo_r1 = pin((uint32_t)p1);
     }
 
+    template <int ROUNDS = 10>
     __device__ __forceinline__ uint4 block(uint32_t b, const PhiloxKeys& k) const {
         // round 0 (c0 = plo, c1 = phi, c2 = b, c3 = s): the products are invariant or uniform
         const uint64_t u1 = (uint64_t)kPhiloxM1 * b;                     // uniform datapath
@@ -97,7 +98,7 @@ struct PairStream {
             // c2 below
             uint32_t c2 = n2;
 #pragma unroll
-            for (int r = 2; r < 10; ++r) {
+            for (int r = 2; r < ROUNDS; ++r) {
                 const uint64_t q0 = (uint64_t)kPhiloxM0 * c0;
                 const uint64_t q1 = (uint64_t)kPhiloxM1 * c2;
                 const uint32_t m0 = (uint32_t)(q1 >> 32) ^ c1 ^ k.k0[r];

@@ -65,7 +65,6 @@ class ComputeDevicePool:
         self._contexts = [_lib.context(d.id) for d in self._ordered]
         self._comms: tp.Optional[tp.List[ctypes.c_void_p]] = None
         self._threads: tp.Optional[ThreadPoolExecutor] = None
-        self._epoch = 0
 
     # ---- reference surface ------------------------------------------------
     @property
@@ -85,9 +84,8 @@ class ComputeDevicePool:
             ctx.sync()
 
     def _run_batches(self, f, h2d, d2h, args_list, kwargs_list):
-        parent_seed, _ = _random.get_state()
-        epoch = self._epoch
-        self._epoch += 1
+        parent_seed = _random.get_seed()
+        epoch = _random.next_subsequence()      # a fan-out consumes one launch slot of the parent stream
         devices = self._ordered
 
         def synced_f(index, args, kwargs):

@@ -202,21 +202,23 @@ def estimate_pi(n, batches=1, draw=None):
 def philox_half_normals(R, seed, subsequence, pair_offset=0):
     """Returns half_normals(step) reproducing the fused kernel's draws.
 
-    Pair p (global index pair_offset + p) at Euler step t (0-based) uses words
-    (2*(t%2), 2*(t%2)+1) of Philox(index=pair, block=t//2, subsequence).
+    One Philox block feeds three Euler steps (cocos_b200/csrc/heston_fused.cu: split_draws).  Pair p (global
+    index pair_offset + p) at Euler step t (0-based) uses block t//3 of Philox(index=pair, block, subsequence);
+    with j = t % 3 and words (w0, w1, w2, w3):
+      radius mantissa (23 bits) = w_j >> 9
+      angle  mantissa (19 bits) = (w_j & 0x1ff) << 10 | (w3 >> (22 - 10 j)) & 0x3ff, placed at mantissa bits [22:4]
     """
     H = (R + 1) // 2
     idx = np.arange(H, dtype=np.uint64) + np.uint64(pair_offset)
     cache = {}
 
     def half_normals(step):
-        blk = step // 2
+        blk, j = divmod(step, 3)
         if blk not in cache:
             cache.clear()
             cache[blk] = px.philox_block(idx, blk, subsequence, seed)
-        o = cache[blk]
-        lane = 2 * (step % 2)
-        z0, z1 = px.box_muller_f64(o[lane], o[lane + 1])
+        w = cache[blk]
+        z0, z1 = px.box_muller_f64_from_fields(w[j] >> np.uint32(9), px.angle19(w[j], w[3], j))
         return np.stack([z0, z1], axis=1)
     return half_normals
 

@@ -20,6 +20,9 @@ Stream layout (shared with cocos_b200/csrc/philox.cuh, documented in DESIGN.md):
   radius   U       = 2 - asfloat(0x3f800000 | (o >> 9))      in (0,1]
   angle    theta   = 2*pi*asfloat(0x3f800000 | (o' >> 9)) - 3*pi   in [-pi,pi)
   normals  z0 = sqrt(-2 ln U) cos(theta),  z1 = sqrt(-2 ln U) sin(theta)
+The array kernels (rand/randn) draw two Box-Muller pairs per block from (o0,o1) and (o2,o3); the fused Heston
+kernel splits one block into THREE steps: 23-bit radius from w_j >> 9, 19-bit angle from w_j[8:0]:w3 bits
+(angle19 / box_muller_f64_from_fields below).
 """
 import numpy as np
 
@@ -96,6 +99,23 @@ def box_muller_f64(o_radius, o_angle):
     U = 2.0 - mantissa_float(o_radius).astype(np.float64)           # (0,1]
     t = mantissa_float(o_angle).astype(np.float64)                   # [1,2)
     theta = 2.0 * np.pi * t - 3.0 * np.pi                            # [-pi,pi)
+    r = np.sqrt(-2.0 * np.log(U))
+    return r * np.cos(theta), r * np.sin(theta)
+
+
+def angle19(w_j, w3, j):
+    """19-bit angle field of Euler step j (0..2) of a Philox block: w_j[8:0] : w3[31-10j : 22-10j]."""
+    w_j = np.asarray(w_j, dtype=np.uint32)
+    w3 = np.asarray(w3, dtype=np.uint32)
+    return ((w_j & np.uint32(0x1FF)) << np.uint32(10)) | ((w3 >> np.uint32(22 - 10 * j)) & np.uint32(0x3FF))
+
+
+def box_muller_f64_from_fields(radius23, angle19_field):
+    """Box-Muller from a 23-bit radius mantissa and a 19-bit angle field (fused kernel, float64 model)."""
+    t_r = ((np.asarray(radius23, dtype=np.uint32)) | np.uint32(0x3F800000)).view(np.float32)
+    t_a = ((np.asarray(angle19_field, dtype=np.uint32) << np.uint32(4)) | np.uint32(0x3F800000)).view(np.float32)
+    U = 2.0 - t_r.astype(np.float64)
+    theta = 2.0 * np.pi * t_a.astype(np.float64) - 3.0 * np.pi
     r = np.sqrt(-2.0 * np.log(U))
     return r * np.cos(theta), r * np.sin(theta)
 
