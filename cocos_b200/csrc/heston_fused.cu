@@ -31,14 +31,30 @@ __device__ __forceinline__ double root(double v) { return sqrt(v); }
 __device__ __forceinline__ float exp_real(float x) { return mufu_ex2(x * 1.4426950408889634f); }
 __device__ __forceinline__ double exp_real(double x) { return exp(x); }
 
-// launch constants the time loop reads every step, held in registers (see pin())
+// Launch constants the time loop reads every step.  The variance is carried as u = c1*v with
+// c1 = -2 ln2 dt < 0, so that v*r^2 = v*(c1*lg2 U) is ONE multiply (u * lg2 U) per path and step.
 template <typename real>
 struct StepRegs {
-    real drift_v, decay, pull, w0, w1, floor_v;
-    float neg2ln2_dt, two_pi;
-    __device__ __forceinline__ explicit StepRegs(const FusedConsts<real> &c)
-        : drift_v(pin(c.drift_v)), decay(pin(c.decay)), pull(pin(c.pull)), w0(pin(c.w0)), w1(pin(c.w1)),
-          floor_v(c.floor_v), neg2ln2_dt(c.neg2ln2_dt), two_pi(pin(kTwoPi)) {}
+    real drift_u;    // (-0.5 dt)/c1          x += drift_u*u + q*cos
+    real decay;      // 1 - kappa dt          u' = min(decay*u + pull_u + q*g, floor_u)
+    real pull_u;     // c1 * kappa v_bar dt
+    real g0, g1;     // c1 * sigma_v * (rho, sqrt(1-rho^2))     g = g0*cos + g1*sin
+    real floor_u;    // c1 * eps_f32 (u <= floor_u  <=>  v >= eps)
+    real u0;         // c1 * v0
+    real inv_c1;     // v = u * inv_c1
+    float two_pi;
+    __device__ __forceinline__ explicit StepRegs(const FusedConsts<real> &c) {
+        const real c1 = (real)c.neg2ln2_dt;
+        drift_u = c.drift_v / c1;
+        decay = c.decay;
+        pull_u = c1 * c.pull;
+        g0 = c1 * c.w0;
+        g1 = c1 * c.w1;
+        floor_u = c1 * c.floor_v;
+        u0 = c1 * c.v0;
+        inv_c1 = (real)1 / c1;
+        two_pi = kTwoPi;
+    }
 };
 
 // The draws of one Euler step: two floats in [1,2) built from random mantissa bits (no I2F: it shares the XU pipe).
@@ -48,39 +64,46 @@ struct StepDraw {
 };
 
 // One Philox4x32-10 block (128 bits) feeds THREE Euler steps (126 bits used): the 32x32->64 multiplies of Philox
-// (IMAD.WIDE: 4 issue cycles each on the FMA pipe, not overlappable with FP32 work) are the most expensive
-// non-MUFU instructions of the loop, so the block is used to the last bit.
+// (IMAD.WIDE: 4 issue cycles each, during which the sub-partition issues nothing else) are the most expensive
+// instructions of the loop, so the block is used to the last bit.
 //   step j (j = 0,1,2): radius <- w_j[31:9];  angle <- w_j[8:0] : w3[31-10j : 22-10j]
-__device__ __forceinline__ void split_draws(const uint4 &o, StepDraw &d0, StepDraw &d1, StepDraw &d2) {
-    constexpr uint32_t kMask = 0x007FFFF0u, kOne = 0x3F800000u;
+// (x & 0x007FFFF0) | one_bits as ONE LOP3: with two immediates ptxas emits two, so the exponent pattern
+// 0x3F800000 travels in a register whose value ptxas cannot fold (see StepRegs::one_bits).
+__device__ __forceinline__ float angle_float(uint32_t x, uint32_t one_bits) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, 0x007FFFF0, %2, 0xEA;" : "=r"(r) : "r"(x), "r"(one_bits));   // (a & b) | c
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void split_draws(const uint4 &o, uint32_t one_bits, StepDraw &d0, StepDraw &d1,
+                                            StepDraw &d2) {
     d0.t_radius = mantissa_float(o.x);
     d1.t_radius = mantissa_float(o.y);
     d2.t_radius = mantissa_float(o.z);
     // funnel shift: upper word of (w_j : w3 << 10j) << 14 has w_j[8:0] : w3 bits in its low 23 bits
-    d0.t_angle = __uint_as_float((__funnelshift_l(o.w, o.x, 14) & kMask) | kOne);
-    d1.t_angle = __uint_as_float((__funnelshift_l(o.w << 10, o.y, 14) & kMask) | kOne);
-    d2.t_angle = __uint_as_float((__funnelshift_l(o.w << 20, o.z, 14) & kMask) | kOne);
+    d0.t_angle = angle_float(__funnelshift_l(o.w, o.x, 14), one_bits);
+    d1.t_angle = angle_float(__funnelshift_l(o.w << 10, o.y, 14), one_bits);
+    d2.t_angle = angle_float(__funnelshift_l(o.w << 20, o.z, 14), one_bits);
 }
 
-// One Euler step of an antithetic pair from one (radius, angle) word pair.
+// One Euler step of an antithetic pair from one (radius, angle) draw.
 //
 // With r^2 = -2 dt ln U and (c, s) = (cos, sin)(theta) the reference needs sqrt(v)*dB0 = sqrt(v)*r*c and
 // sqrt(v)*(rho dB0 + rho' dB1) = sqrt(v)*r*(rho c + rho' s).  Since sqrt(v)*r = sqrt(v*r^2), the radius never has to
-// be formed: q = MUFU.SQRT(v * r^2) replaces MUFU.SQRT(r^2) and MUFU.SQRT(v) -- 5 MUFU per pair-step instead of 6,
-// at the same count of FP32 instructions.
+// be formed: q = MUFU.SQRT(v * r^2) replaces MUFU.SQRT(r^2) and MUFU.SQRT(v) -- 5 MUFU per pair-step instead of 6.
+// Per pair-step: 5 MUFU + 15 FP32 + 2 FMNMX.
 template <typename real>
-__device__ __forceinline__ void euler_pair(real &x1, real &v1, real &x2, real &v2, float t_radius, float t_angle,
+__device__ __forceinline__ void euler_pair(real &x1, real &u1, real &x2, real &u2, float t_radius, float t_angle,
                                            const StepRegs<real> &k) {
-    const float U = 2.0f - t_radius;                                      // (0,1]
-    const float r2 = mufu_lg2(U) * k.neg2ln2_dt;                          // (r*sqrt(dt))^2 >= 0
+    const real L = (real)mufu_lg2(2.0f - t_radius);                       // lg2 U <= 0, U in (0,1]
     const float theta = fmaf(t_angle, k.two_pi, -kThreePi);               // [-pi,pi)
     const real cs = (real)mufu_cos(theta), sn = (real)mufu_sin(theta);
-    const real g = fma(cs, k.w0, sn * k.w1);                              // sigma_v*(rho c + rho' s)
-    const real q1 = root(v1 * (real)r2), q2 = root(v2 * (real)r2);        // sqrt(v)*r*sqrt(dt)
-    x1 = fma(q1, cs, fma(v1, k.drift_v, x1));
-    x2 = fma(q2, -cs, fma(v2, k.drift_v, x2));
-    v1 = fmax(fma(q1, g, fma(v1, k.decay, k.pull)), k.floor_v);
-    v2 = fmax(fma(q2, -g, fma(v2, k.decay, k.pull)), k.floor_v);
+    const real g = fma(cs, k.g0, sn * k.g1);                              // c1*sigma_v*(rho c + rho' s)
+    const real q1 = root(u1 * L), q2 = root(u2 * L);                      // sqrt(v*r^2) = sqrt(v)*r*sqrt(dt)
+    x1 = fma(q1, cs, fma(u1, k.drift_u, x1));
+    x2 = fma(q2, -cs, fma(u2, k.drift_u, x2));
+    u1 = fmin(fma(q1, g, fma(u1, k.decay, k.pull_u)), k.floor_u);
+    u2 = fmin(fma(q2, -g, fma(u2, k.decay, k.pull_u)), k.floor_u);
 }
 
 template <int N>
@@ -122,6 +145,8 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
     double acc_sq[MULTI ? 2 : 1] = {};
     const real x_shift = c.x0 + (real)c.steps * c.mu_dt;
     const StepRegs<real> k(c);
+    // 0x3F800000 in a register ptxas cannot constant-fold (steps < 2^31 always): keeps angle_float at one LOP3
+    const uint32_t one_bits = 0x3F800000u | (c.steps >> 31);
     PhiloxKeys keys;   // round keys in registers: ptxas otherwise re-loads them from the constant bank every call
 #pragma unroll
     for (int r = 0; r < 10; ++r) { keys.k0[r] = pin(c.keys.k0[r]); keys.k1[r] = pin(c.keys.k1[r]); }
@@ -139,7 +164,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             paired[q] = active[q] && gp < c.partnered;
             rng[q].init((uint32_t)gp, (uint32_t)(gp >> 32), c.subsequence, c.keys);
             x1[q] = x2[q] = (real)0;
-            v1[q] = v2[q] = c.v0;
+            v1[q] = v2[q] = k.u0;            // v1/v2 hold u = c1*v inside the time loop
         }
         if constexpr (TRAJ) {   // row 0: the initial log price
 #pragma unroll
@@ -188,13 +213,14 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             uint4 cur[PPT];
 #pragma unroll
             for (int q = 0; q < PPT; ++q) cur[q] = rng[q].template block<ROUNDS>(0u, keys);
+#pragma unroll(MINB == 1 ? 2 : 1)
             for (uint32_t b = 0; b < calls; ++b) {
                 uint4 nxt[PPT];
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) {
                     nxt[q] = rng[q].template block<ROUNDS>(b + 1, keys);
-                    split_draws(cur[q], d0[q], d1[q], d2[q]);
+                    split_draws(cur[q], one_bits, d0[q], d1[q], d2[q]);
                 }
                 advance(d0, 3 * b + 1);
                 advance(d1, 3 * b + 2);
@@ -205,7 +231,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             if (rest) {
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
 #pragma unroll
-                for (int q = 0; q < PPT; ++q) split_draws(cur[q], d0[q], d1[q], d2[q]);
+                for (int q = 0; q < PPT; ++q) split_draws(cur[q], one_bits, d0[q], d1[q], d2[q]);
                 advance(d0, 3 * calls + 1);
                 if (rest > 1) advance(d1, 3 * calls + 2);
             }
@@ -213,7 +239,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             for (uint32_t b = 0; b < calls + (rest ? 1u : 0u); ++b) {
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
 #pragma unroll
-                for (int q = 0; q < PPT; ++q) split_draws(rng[q].template block<ROUNDS>(b, keys), d0[q], d1[q], d2[q]);
+                for (int q = 0; q < PPT; ++q) split_draws(rng[q].template block<ROUNDS>(b, keys), one_bits, d0[q], d1[q], d2[q]);
                 const uint32_t left = c.steps - 3 * b;
                 advance(d0, 3 * b + 1);
                 if (left > 1) advance(d1, 3 * b + 2);
@@ -226,8 +252,8 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
         for (int q = 0; q < PPT; ++q) {
             const real xT1 = x1[q] + x_shift, xT2 = x2[q] + x_shift;
             if (x_out != nullptr) {
-                if (active[q]) { x_out[local[q]] = xT1; v_out[local[q]] = v1[q]; }
-                if (paired[q]) { x_out[c.pair_count + local[q]] = xT2; v_out[c.pair_count + local[q]] = v2[q]; }
+                if (active[q]) { x_out[local[q]] = xT1; v_out[local[q]] = v1[q] * k.inv_c1; }
+                if (paired[q]) { x_out[c.pair_count + local[q]] = xT2; v_out[c.pair_count + local[q]] = v2[q] * k.inv_c1; }
             }
             const real S1 = exp_real(xT1), S2 = exp_real(xT2);
             if constexpr (!MULTI) {

@@ -47,8 +47,9 @@ def test_randn_close_to_model(cn, n):
     cn.random.seed(5)
     z = cn.random.randn(n).to_numpy()
     model = px.randn_f32_model(n, 5, 0)
-    # MUFU lg2/sqrt/sin/cos against float64: absolute 2e-6 + relative 2e-6
-    np.testing.assert_allclose(z, model, rtol=2e-6, atol=2e-6)
+    # MUFU lg2/sqrt/sin/cos against float64.  lg2.approx has ~2^-22 ABSOLUTE error, so for U close to 1 (small
+    # radius r) the error of r = sqrt(-2 ln U) is ~3e-7/(2r): up to ~1e-5 at the r ~ 0.02 seen in 2e5 draws.
+    np.testing.assert_allclose(z, model, rtol=1e-5, atol=2e-5)
     z64 = cn.random.randn(n, dtype=np.float64).to_numpy()
     np.testing.assert_allclose(z64, px.randn_f64_model(n, 5, 1), rtol=1e-12, atol=1e-13)
 
@@ -100,7 +101,7 @@ def test_antithetic_layout(cn, shape, axis, dtype):
         draw_n, draw_u = px.randn_f64_model(n_draw, 77, 0), px.rand_f64(n_draw, 77, 1)
     want_n = hn.normal_antithetic(shape, axis, dtype, draw=lambda *s: draw_n.reshape(s))
     want_u = hn.uniform_antithetic(shape, axis, dtype, draw=lambda *s: draw_u.reshape(s))
-    tol = dict(rtol=2e-6, atol=2e-6) if dtype == np.float32 else dict(rtol=1e-12, atol=1e-13)
+    tol = dict(rtol=1e-5, atol=2e-5) if dtype == np.float32 else dict(rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(zn, want_n, **tol)
     assert np.array_equal(un, want_u)                    # uniforms and 1-u are exact
     # the reflection is exact on the device output itself
