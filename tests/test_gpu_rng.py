@@ -12,6 +12,18 @@ def cn(gpu_device):
     return cn
 
 
+def assert_close_to_box_muller_model(z, model):
+    """MUFU lg2/sqrt/sin/cos against the float64 model of the same bits.
+
+    lg2.approx has ~2^-22 ABSOLUTE error, so for U within a few ulps of 1 (radius r ~ 1e-3, probability ~1e-6 per
+    draw) r = sqrt(-2 ln U) is off by up to ~1e-4; everywhere else the error is a few 1e-6.
+    """
+    diff = np.abs(z.astype(np.float64) - model)
+    assert diff.max() < 1e-3
+    assert np.mean(diff > 2e-5 + 1e-5 * np.abs(model)) <= 2e-5
+    assert np.median(diff) < 2e-7
+
+
 def test_philox_known_answers_on_device(cn, golden_values):
     zero = cn.random.philox_words(1, first_index=0, block=0, subsequence=0, seed_value=0).to_numpy()[0]
     assert [f"{w:08x}" for w in zero] == golden_values["philox_kat"][0]["out"]
@@ -47,9 +59,7 @@ def test_randn_close_to_model(cn, n):
     cn.random.seed(5)
     z = cn.random.randn(n).to_numpy()
     model = px.randn_f32_model(n, 5, 0)
-    # MUFU lg2/sqrt/sin/cos against float64.  lg2.approx has ~2^-22 ABSOLUTE error, so for U close to 1 (small
-    # radius r) the error of r = sqrt(-2 ln U) is ~3e-7/(2r): up to ~1e-5 at the r ~ 0.02 seen in 2e5 draws.
-    np.testing.assert_allclose(z, model, rtol=1e-5, atol=2e-5)
+    assert_close_to_box_muller_model(z, model)
     z64 = cn.random.randn(n, dtype=np.float64).to_numpy()
     np.testing.assert_allclose(z64, px.randn_f64_model(n, 5, 1), rtol=1e-12, atol=1e-13)
 
@@ -101,8 +111,10 @@ def test_antithetic_layout(cn, shape, axis, dtype):
         draw_n, draw_u = px.randn_f64_model(n_draw, 77, 0), px.rand_f64(n_draw, 77, 1)
     want_n = hn.normal_antithetic(shape, axis, dtype, draw=lambda *s: draw_n.reshape(s))
     want_u = hn.uniform_antithetic(shape, axis, dtype, draw=lambda *s: draw_u.reshape(s))
-    tol = dict(rtol=1e-5, atol=2e-5) if dtype == np.float32 else dict(rtol=1e-12, atol=1e-13)
-    np.testing.assert_allclose(zn, want_n, **tol)
+    if dtype == np.float32:
+        assert_close_to_box_muller_model(zn, want_n)
+    else:
+        np.testing.assert_allclose(zn, want_n, rtol=1e-12, atol=1e-13)
     assert np.array_equal(un, want_u)                    # uniforms and 1-u are exact
     # the reflection is exact on the device output itself
     sl = hn.antithetic_slices(shape, axis)
