@@ -1,0 +1,87 @@
+"""Multi-GPU shard (needs >= 2 devices; skipped otherwise): disjoint pair ranges per GPU + ONE NCCL allreduce.
+
+The correctness property is device-count invariance: every pair's Philox counter depends on its global index
+only, so G GPUs reproduce the 1-GPU sums up to fp64 summation order."""
+import json
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_count():
+    try:
+        from cocos_b200 import _lib
+        return _lib.device_count()
+    except Exception:       # noqa: BLE001
+        return 0
+
+
+needs2 = pytest.mark.skipif(_device_count() < 2, reason="needs at least 2 GPUs")
+
+
+@needs2
+def test_pool_sums_are_device_count_invariant(gpu_device, ref_params):
+    from cocos_b200 import _lib
+    from cocos_b200.multi_processing import ComputeDevicePool
+    q = ref_params
+    p = _lib.HestonParams(q["T"], q["r"], q["kappa"], q["v_bar"], q["sigma_v"], q["rho"], q["x0"], q["v0"])
+    R, N, strikes = 4_000_001, 101, [0.9, 0.95, 1.0]
+    n = _device_count()
+    one = ComputeDevicePool(compute_devices=[0])
+    s1, q1 = one.heston_sums(p, R, N, strikes, seed=5, subsequence=3)
+    for g in sorted({2, n}):
+        pool = ComputeDevicePool(compute_devices=list(range(g)))
+        assert pool.number_of_devices == g
+        sg, qg = pool.heston_sums(p, R, N, strikes, seed=5, subsequence=3)
+        np.testing.assert_allclose(sg, s1, rtol=1e-12)
+        np.testing.assert_allclose(qg, q1, rtol=1e-12)
+        s64, _ = pool.heston_sums(p, R // 4, N, strikes, seed=5, subsequence=3, dtype_suffix="f64")
+        o64, _ = one.heston_sums(p, R // 4, N, strikes, seed=5, subsequence=3, dtype_suffix="f64")
+        np.testing.assert_allclose(s64, o64, rtol=1e-12)
+        pool.close()
+    one.close()
+
+
+@needs2
+def test_reference_multi_gpu_entry_point(gpu_device, golden_values, ref_params):
+    """simulate_and_compute_option_price_gpu with a pool (heston_utilities.py:217-270 call pattern)."""
+    from cocos_b200 import heston
+    from cocos_b200.multi_processing import ComputeDevicePool
+    from cocos_b200.numerics import random as rnd
+    pool = ComputeDevicePool()
+    rnd.seed(11)
+    price = heston.simulate_and_compute_option_price_gpu(nT=501, R=4_000_000, compute_device_pool=pool, **ref_params)
+    ref = golden_values["statistical"]["nT501"]
+    assert abs(price - ref["price"]) <= 3 * math.hypot(ref["se"], ref["se"] / 2)
+    # generic map_reduce across devices: batch i on device i mod G, ordered fold
+    devs = pool.map_reduce(f=lambda: __import__("cocos_b200").device.ComputeDeviceManager.get_current_compute_device_id(),
+                           reduction=lambda acc, d: acc + [d], initial_value=[], number_of_batches=5)
+    G = pool.number_of_devices
+    assert devs == [i % G for i in range(5)]
+    pool.close()
+
+
+@needs2
+def test_torchrun_bench_two_ranks(golden_values):
+    """bench.py under torchrun: one rank per GPU, NCCL allreduce inside the C library."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "3",
+           "--warmup", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                  # rank 0 only
+    res = json.loads(lines[0])
+    assert res["n_gpus"] == 2 and res["config"]["paths"] == 20_000_000
+    ref = golden_values["statistical"]["nT501"]
+    assert abs(res["price"] - ref["price"]) <= 3 * math.hypot(res["price_se"], ref["se"])
+    assert abs(res["e2e"]["price"] - ref["price"]) <= 3 * math.hypot(res["price_se"], ref["se"])

@@ -1,0 +1,131 @@
+"""Secondary kernels on one B200: achieved rates against their rooflines (HBM for the materialising kernels).
+
+python tools/bench_aux.py [out.json]
+"""
+import ctypes
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cocos_b200 import _lib, device, heston, monte_carlo_pi  # noqa: E402
+from cocos_b200.numerics import random as rnd  # noqa: E402
+from cocos_b200.numerics._array import empty_on  # noqa: E402
+
+P = dict(x0=0.0, v0=0.101 ** 2, r=math.log(1.0319), rho=-0.7, sigma_v=0.61, kappa=6.21, v_bar=0.019, T=1.0)
+HP = _lib.HestonParams(P["T"], P["r"], P["kappa"], P["v_bar"], P["sigma_v"], P["rho"], P["x0"], P["v0"])
+
+
+def timed(ctx, fn, reps=5):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        ctx.timer_start()
+        fn()
+        best = min(best, ctx.timer_stop())
+    return best
+
+
+def main():
+    out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/aux.json"
+    device.init(device_id=0)
+    ctx = device.current_context()
+    L = _lib.lib()
+    res = {}
+
+    def peak(kind):
+        ops, ms = ctypes.c_double(0), ctypes.c_float(0)
+        _lib.check(L.cb_peak_measure(ctx.handle, kind, 3, ctypes.byref(ops), ctypes.byref(ms)))
+        return ops.value
+    hbm_w, hbm_c, dfma = peak(8), peak(10), peak(6)
+    res["peaks"] = {"hbm_write_GBs": hbm_w / 1e9, "hbm_copy_GBs": hbm_c / 1e9, "dfma_per_s": dfma}
+
+    # ---- random arrays (HBM-write bound)
+    n = 1 << 30
+    for name, dtype, item in (("randn_f32", np.float32, 4), ("rand_f32", np.float32, 4), ("randn_f64", np.float64, 8),
+                              ("rand_f64", np.float64, 8)):
+        m = n if item == 4 else n // 2
+        buf = empty_on(ctx, (m,), dtype)
+        fn = getattr(L, "cb_" + name)
+        ms = timed(ctx, lambda: _lib.check(fn(ctx.handle, buf.data_ptr, m, 1, 0)))
+        res[name] = {"elements": m, "ms": ms, "GBs": m * item / ms / 1e6, "frac_hbm_write": m * item / ms / 1e6 / (hbm_w / 1e9)}
+        del buf
+    R = 200_000_000
+    buf = empty_on(ctx, (R, 2), np.float32)
+    dims = (ctypes.c_uint64 * 2)(R, 2)
+    ms = timed(ctx, lambda: _lib.check(L.cb_randn_antithetic_f32(ctx.handle, buf.data_ptr, dims, 2, 0, 1, 0)))
+    res["randn_antithetic_f32_(2e8,2)"] = {"ms": ms, "GBs": R * 8 / ms / 1e6, "frac_hbm_write": R * 8 / ms / 1e6 / (hbm_w / 1e9)}
+    del buf
+
+    # ---- parity kernel (HBM-read bound): BASELINE C1 and a larger instance
+    for Rr, N in ((100_000, 101), (4_000_000, 101)):
+        H = (Rr + 1) // 2
+        Z = empty_on(ctx, (N - 1, H, 2), np.float32)
+        _lib.check(L.cb_randn_f32(ctx.handle, Z.data_ptr, Z.size, 3, 0))
+        x, v = empty_on(ctx, (Rr,), np.float32), empty_on(ctx, (Rr,), np.float32)
+        ms = timed(ctx, lambda: _lib.check(L.cb_heston_terminal_injected_f32(ctx.handle, Z.data_ptr, ctypes.byref(HP), Rr, N, x.data_ptr, v.data_ptr)))
+        byts = Z.size * 4
+        res[f"injected_f32_R{Rr}_N{N}"] = {"ms": ms, "path_steps_per_s": Rr * (N - 1) / ms * 1e3, "GBs_read": byts / ms / 1e6,
+                                           "frac_hbm": byts / ms / 1e6 / (hbm_c / 1e9)}
+        del Z, x, v
+
+    # ---- trajectory (path-materialising) mode: 4 B written per path-step
+    for Rr, N in ((4_000_000, 101), (2_000_000, 501)):
+        rnd.seed(0)
+        t0 = time.perf_counter()
+        x, v, traj = heston.simulate_heston_model(T=P["T"], N=N, R=Rr, mu=P["r"], kappa=P["kappa"], v_bar=P["v_bar"],
+                                                  sigma_v=P["sigma_v"], rho=P["rho"], x0=P["x0"], v0=P["v0"],
+                                                  return_trajectory=True)
+        ctx.sync()
+        k_arr, nK = _lib.strikes_array([0.95])
+        pairs = Rr // 2
+
+        def go():
+            _lib.check(L.cb_heston_price_launch_f32(ctx.handle, ctypes.byref(HP), Rr, N, k_arr, nK, 0, 5, 0, pairs, None,
+                                                    x.data_ptr, v.data_ptr, traj.data_ptr))
+        ms = timed(ctx, go)
+        byts = N * Rr * 4
+        res[f"trajectory_f32_R{Rr}_N{N}"] = {"ms": ms, "path_steps_per_s": Rr * (N - 1) / ms * 1e3, "GBs_written": byts / ms / 1e6,
+                                             "frac_hbm_write": byts / ms / 1e6 / (hbm_w / 1e9)}
+        del x, v, traj
+
+    # ---- fused variants: strike sweeps and float64 state (C5 shape per GPU: 12.5M paths x 252 steps, 64 strikes)
+    strikes64 = [0.70 + 0.60 * i / 63 for i in range(64)]
+    for name, sfx, Rr, N, ks in (("fused_f32_1strike_C3", "f32", 10_000_000, 501, [0.95]),
+                                 ("fused_f32_64strikes", "f32", 10_000_000, 501, strikes64),
+                                 ("fused_f32_C4_shard_1000steps", "f32", 10_000_000, 1001, [0.95]),
+                                 ("fused_f64_1strike", "f64", 12_500_000, 253, [0.95]),
+                                 ("fused_f64_64strikes_C5_shard", "f64", 12_500_000, 253, strikes64)):
+        k_arr, nK = _lib.strikes_array(ks)
+        launch = getattr(L, f"cb_heston_price_launch_{sfx}")
+
+        def go():
+            _lib.check(launch(ctx.handle, ctypes.byref(HP), Rr, N, k_arr, nK, 0, 9, 0, (Rr + 1) // 2, None, None, None, None))
+        ms = timed(ctx, go)
+        res[name] = {"ms": ms, "path_steps_per_s": Rr * (N - 1) / ms * 1e3}
+
+    # ---- pi (BASELINE config 2)
+    rnd.seed(0)
+    for anti in (True, False):
+        nn = 1_000_000_000
+        ndraw = (nn + 1) // 2 if anti else nn
+
+        def go():
+            _lib.check(L.cb_pi_count_launch(ctx.handle, nn, 0, 1, int(anti), 0, ndraw, None))
+        ms = timed(ctx, go)
+        inside = ctypes.c_uint64(0)
+        _lib.check(L.cb_pi_count_finish(ctx.handle, ctypes.byref(inside)))
+        res[f"pi_1e9_{'antithetic' if anti else 'plain'}"] = {"ms": ms, "points_per_s": nn / ms * 1e3, "pi": 4 * inside.value / nn}
+
+    for k, v in res.items():
+        print(k, json.dumps(v))
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    json.dump(res, open(out_path, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
