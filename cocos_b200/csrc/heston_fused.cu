@@ -27,7 +27,20 @@ constexpr int kMaxWarps = kMaxThreads / 32;
 // ---- per-type math ---------------------------------------------------------
 
 __device__ __forceinline__ float root(float v) { return mufu_sqrt(v); }
-__device__ __forceinline__ double root(double v) { return sqrt(v); }
+// double sqrt without the IEEE fix-up path: MUFU.RSQ64H seed (~2^-22) + ONE cubically convergent step on 1/sqrt,
+//   e = 1 - p y^2,  y' = y (1 + e/2 + 3 e^2/8)   =>  relative error ~ e^3 ~ 2^-66  (the parity kernel keeps __dsqrt_rn).
+// FP64 instructions cost two issue cycles each on B200, so the step count matters: 7 FP64 + 1 MUFU, no F2F
+// (conversions to/from f64 share the XU pipe).  p = 0 (U = 1) is nudged to 1e-290 so that the seed stays finite.
+__device__ __forceinline__ double root(double p) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p + 1e-290));
+    const double e = fma(-(p * y), y, 1.0);
+    y = fma(y, e * fma(e, 0.375, 0.5), y);
+    return p * y;
+}
+// min without the NaN bookkeeping of fmin(double) (DSETP + 2 SEL instead of 6 instructions)
+__device__ __forceinline__ float floor_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double floor_min(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ float exp_real(float x) { return mufu_ex2(x * 1.4426950408889634f); }
 __device__ __forceinline__ double exp_real(double x) { return exp(x); }
 
@@ -38,7 +51,7 @@ struct StepRegs {
     real drift_u;    // (-0.5 dt)/c1          x += drift_u*u + q*cos
     real decay;      // 1 - kappa dt          u' = min(decay*u + pull_u + q*g, floor_u)
     real pull_u;     // c1 * kappa v_bar dt
-    real g0, g1;     // c1 * sigma_v * (rho, sqrt(1-rho^2))     g = g0*cos + g1*sin
+    float g0f, g1f;  // c1 * sigma_v * (rho, sqrt(1-rho^2))     g = g0*cos + g1*sin
     real floor_u;    // c1 * eps_f32 (u <= floor_u  <=>  v >= eps)
     real u0;         // c1 * v0
     real inv_c1;     // v = u * inv_c1
@@ -48,8 +61,8 @@ struct StepRegs {
         drift_u = c.drift_v / c1;
         decay = c.decay;
         pull_u = c1 * c.pull;
-        g0 = c1 * c.w0;
-        g1 = c1 * c.w1;
+        g0f = (float)(c1 * c.w0);
+        g1f = (float)(c1 * c.w1);
         floor_u = c1 * c.floor_v;
         u0 = c1 * c.v0;
         inv_c1 = (real)1 / c1;
@@ -97,13 +110,15 @@ __device__ __forceinline__ void euler_pair(real &x1, real &u1, real &x2, real &u
                                            const StepRegs<real> &k) {
     const real L = (real)mufu_lg2(2.0f - t_radius);                       // lg2 U <= 0, U in (0,1]
     const float theta = fmaf(t_angle, k.two_pi, -kThreePi);               // [-pi,pi)
-    const real cs = (real)mufu_cos(theta), sn = (real)mufu_sin(theta);
-    const real g = fma(cs, k.g0, sn * k.g1);                              // c1*sigma_v*(rho c + rho' s)
+    const float cs_f = mufu_cos(theta), sn_f = mufu_sin(theta);
+    const real cs = (real)cs_f;
+    const real g = (real)fmaf(cs_f, k.g0f, sn_f * k.g1f);                 // c1*sigma_v*(rho c + rho' s), float accuracy
+                                                                          // is all the MUFU inputs have anyway
     const real q1 = root(u1 * L), q2 = root(u2 * L);                      // sqrt(v*r^2) = sqrt(v)*r*sqrt(dt)
     x1 = fma(q1, cs, fma(u1, k.drift_u, x1));
     x2 = fma(q2, -cs, fma(u2, k.drift_u, x2));
-    u1 = fmin(fma(q1, g, fma(u1, k.decay, k.pull_u)), k.floor_u);
-    u2 = fmin(fma(q2, -g, fma(u2, k.decay, k.pull_u)), k.floor_u);
+    u1 = floor_min(fma(q1, g, fma(u1, k.decay, k.pull_u)), k.floor_u);
+    u2 = floor_min(fma(q2, -g, fma(u2, k.decay, k.pull_u)), k.floor_u);
 }
 
 template <int N>
