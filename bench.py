@@ -105,8 +105,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3 Heston European call 10M paths x 500 steps f32 (bounded CPU sample per step)",
-                   "paths_per_step": batches * arm.batch_paths, "nT": arm.nT},
+        "config": {"workload": "C3 Heston European call, 10M paths x 500 steps fp32 (CPU arm: bounded sample of "
+                               f"{batches * arm.batch_paths} paths per step)",
+                   "paths": batches * arm.batch_paths, "nT": arm.nT, "antithetic": True},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
                          "sample": arm.describe(batches) + f", {args.steps} steps", "cpu": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -252,8 +253,12 @@ def run_b200(args):
         arm = CpuArm()
         batches = 2 * arm.cores
         v, dt, cpu_price = arm.step(batches, seed0=777)
+        t1 = time.perf_counter()
+        _cpu_batch((778, arm.batch_paths, arm.nT))                       # one batch in this process: 1 core
+        one_core = arm.batch_paths * (arm.nT - 1) / (time.perf_counter() - t1)
         cpu = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": "port",
-               "sample": arm.describe(batches) + f" ({dt:.1f} s)", "cpu": cpu_model(), "price": cpu_price}
+               "sample": arm.describe(batches) + f" ({dt:.1f} s)", "cpu": cpu_model(), "price": cpu_price,
+               "value_1core": one_core}
         arm.close()
 
     if rank == 0:

@@ -181,12 +181,18 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             x1[q] = x2[q] = (real)0;
             v1[q] = v2[q] = k.u0;            // v1/v2 hold u = c1*v inside the time loop
         }
+        real *row1 = nullptr, *row2 = nullptr;      // this thread's slots in the current trajectory row
+        int store_mode = 0;
+        uint32_t edge_mask = 0;                      // bit q: pair q active, bit 4+q: partner of pair q exists
         if constexpr (TRAJ) {   // row 0: the initial log price
+            row1 = traj + local[0];
+            row2 = traj + c.pair_count + local[0];
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
-                if (active[q]) traj[local[q]] = c.x0;
-                if (paired[q]) traj[c.pair_count + local[q]] = c.x0;
+                if (active[q]) { row1[q] = c.x0; edge_mask |= 1u << q; }
+                if (paired[q]) { row2[q] = c.x0; edge_mask |= 16u << q; }
             }
+            store_mode = (vec_ok && edge_mask == 0xFFu) ? 1 : (edge_mask ? 2 : 0);
         }
 
         // one Euler step for every pair of this thread from one (radius, angle) word pair each
@@ -196,24 +202,22 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
                 euler_pair(x1[q], v1[q], x2[q], v2[q], d[q].t_radius, d[q].t_angle, k);
             }
             if constexpr (TRAJ) {
+                // row pointers advance by one row per step; the store mode was fixed once per pair block:
+                // 1 = all four pairs active and partnered, aligned: two 16-byte stores; 2 = ragged edge: scalar
                 const real shift = c.x0 + (real)step_no * c.mu_dt;
-                real *row = traj + (uint64_t)step_no * row_len;
-                if (vec_ok && active[PPT - 1]) {
+                row1 += row_len;
+                row2 += row_len;
+                if (store_mode == 1) {
                     real a[PPT], b[PPT];
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) { a[q] = x1[q] + shift; b[q] = x2[q] + shift; }
-                    PairStore<PPT>::put(row + local[0], a);
-                    if (paired[PPT - 1]) {
-                        PairStore<PPT>::put(row + c.pair_count + local[0], b);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < PPT; ++q) if (paired[q]) row[c.pair_count + local[q]] = b[q];
-                    }
-                } else {
+                    PairStore<PPT>::put(row1, a);
+                    PairStore<PPT>::put(row2, b);
+                } else if (store_mode == 2) {
 #pragma unroll
                     for (int q = 0; q < PPT; ++q) {
-                        if (active[q]) row[local[q]] = x1[q] + shift;
-                        if (paired[q]) row[c.pair_count + local[q]] = x2[q] + shift;
+                        if (edge_mask & (1u << q)) row1[q] = x1[q] + shift;
+                        if (edge_mask & (16u << q)) row2[q] = x2[q] + shift;
                     }
                 }
             }
@@ -228,7 +232,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             uint4 cur[PPT];
 #pragma unroll
             for (int q = 0; q < PPT; ++q) cur[q] = rng[q].template block<ROUNDS>(0u, keys);
-#pragma unroll(MINB == 1 ? 2 : 1)
+#pragma unroll((MINB == 1 && !TRAJ) ? 2 : 1)
             for (uint32_t b = 0; b < calls; ++b) {
                 uint4 nxt[PPT];
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
@@ -391,7 +395,7 @@ template <typename real>
 cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s, ReduceWorkspace ws,
                                 real *d_x, real *d_v, real *d_traj, cudaStream_t stream) {
     const bool multi = c.nK > 1;
-    if (d_traj != nullptr) return launch_one<real, 4, true, true>(c, s, ws, d_x, d_v, d_traj, stream);
+    if (d_traj != nullptr) return launch_one<real, 4, true, true, true, 2>(c, s, ws, d_x, d_v, d_traj, stream);
     if constexpr (sizeof(real) == 4) {
         if (!multi && s.variant > 0) {
             void *args[] = {(void *)&c, (void *)&ws, (void *)&d_x, (void *)&d_v, (void *)&d_traj};
@@ -428,7 +432,7 @@ cudaError_t fused_occupancy(int threads, int ppt, bool multi, int variant, int *
     if (ppt == 1) fn = multi ? (const void *)heston_fused_kernel<real, 1, true, false> : (const void *)heston_fused_kernel<real, 1, false, false>;
     else if (ppt == 2) fn = multi ? (const void *)heston_fused_kernel<real, 2, true, false> : (const void *)heston_fused_kernel<real, 2, false, false>;
     else if (ppt == 4) fn = multi ? (const void *)heston_fused_kernel<real, 4, true, false> : (const void *)heston_fused_kernel<real, 4, false, false>;
-    else if (ppt == -4) fn = (const void *)heston_fused_kernel<real, 4, true, true>;
+    else if (ppt == -4) fn = (const void *)heston_fused_kernel<real, 4, true, true, true, 2>;
     else return cudaErrorInvalidValue;
     cudaFuncAttributes attr;
     cudaError_t e = cudaFuncGetAttributes(&attr, fn);

@@ -66,6 +66,29 @@ class B200Bundle(NumericalPackageBundle):
 CocosBundle = B200Bundle
 
 
+class NumpyBundle(NumericalPackageBundle):
+    """numerical_package_bundle.py:60-80 of the reference, kept so that code enumerating bundles still imports.
+    The Heston entry points of this package refuse it: there is no CPU branch here (see oracle/ for the restatement)."""
+
+    @classmethod
+    def is_installed(cls) -> bool:
+        return True
+
+    @classmethod
+    def label(cls) -> str:
+        return 'NumPy'
+
+    @classmethod
+    def module(cls) -> ModuleType:
+        import numpy
+        return numpy
+
+    @classmethod
+    def random_module(cls) -> ModuleType:
+        import numpy.random
+        return numpy.random
+
+
 def get_available_numerical_packages(list_installed_bundles: tp.Optional[bool] = False) \
         -> tp.Tuple[tp.Type[NumericalPackageBundle], ...]:
     bundles = tuple(b for b in (B200Bundle,) if b.is_installed())
