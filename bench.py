@@ -285,7 +285,10 @@ def run_b200(args):
                            else "cocos_b200.distributed.ShardedPricer.price"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "sfu", "achieved": per_gpu * SFU_PER_PATH_STEP / 1e9, "peak": mufu_peak / 1e9,
-                         "unit": "GSFUop/s per GPU", "frac": per_gpu / sfu_roof, "traffic": None,
+                         "unit": "GSFUop/s per GPU", "frac": per_gpu / sfu_roof,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
+                         # (profiles/r01_ncu_fused_f32.md): the kernel's algorithmic DRAM traffic is 0 + 16 B of sums
+                         "traffic": 81920,
                          "peak_source": "MUFU chain kernels (lg2/sqrt/sin, min) timed live on this GPU; "
                                         "MEASURED_PEAKS.json has no SFU/FP32 figure",
                          "kernel": "heston_fused_kernel<float>", "sfu_ops_per_path_step": SFU_PER_PATH_STEP,
