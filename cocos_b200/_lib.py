@@ -55,6 +55,11 @@ PROTOTYPES = {
     "cb_randn_antithetic_f64": (c_int, [c_void_p, c_void_p, P(c_u64), c_int, c_int, c_u64, c_u32]),
     "cb_rand_antithetic_f32": (c_int, [c_void_p, c_void_p, P(c_u64), c_int, c_int, c_u64, c_u32]),
     "cb_rand_antithetic_f64": (c_int, [c_void_p, c_void_p, P(c_u64), c_int, c_int, c_u64, c_u32]),
+    "cb_random_distribution_f32": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_double, c_double, c_u64, c_u32]),
+    "cb_randint": (c_int, [c_void_p, c_void_p, c_int, c_u64, ctypes.c_int64, ctypes.c_int64, c_u64, c_u32]),
+    "cb_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u64, c_int]),
+    "cb_multivariate_normal_f32": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_void_p, c_void_p, c_u64, c_u32]),
+    "cb_multivariate_normal_f64": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_void_p, c_void_p, c_u64, c_u32]),
     "cb_heston_terminal_injected_f32": (c_int, [c_void_p, c_void_p, P(HestonParams), c_u64, c_u32, c_void_p, c_void_p]),
     "cb_heston_terminal_injected_f64": (c_int, [c_void_p, c_void_p, P(HestonParams), c_u64, c_u32, c_void_p, c_void_p]),
     "cb_heston_terminal_injected_host_f32": (c_int, [c_void_p, c_void_p, P(HestonParams), c_u64, c_u32, c_void_p, c_void_p]),

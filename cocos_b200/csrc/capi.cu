@@ -439,6 +439,77 @@ CB_ANTI(cb_randn_antithetic_f64, double, true)
 CB_ANTI(cb_rand_antithetic_f32, float, false)
 CB_ANTI(cb_rand_antithetic_f64, double, false)
 
+// ---------------------------------------------------------------- derived distributions
+
+extern "C" CB_API int cb_random_distribution_f32(cb_ctx *c, float *d_out, uint64_t n, int kind, double a, double b,
+                                                 uint64_t seed, uint32_t subsequence) {
+    int rc = check_out(c, d_out, n);
+    if (rc) return rc;
+    CB_REQUIRE(kind >= 0 && kind <= 7, "unknown distribution kind %d", kind);
+    float fa = (float)a, fb = (float)b;
+    switch (kind) {
+        case 0: CB_REQUIRE(b >= a, "high must not be less than low"); fb = (float)(b - a); break;   // (low, high-low)
+        case 1: CB_REQUIRE(a >= 0.0, "scale must be non-negative"); break;
+        case 2: case 3: case 4: CB_REQUIRE(b >= 0.0, "scale must be non-negative"); break;
+        case 5: CB_REQUIRE(a > 0.0 && b > 0.0, "mean and scale must be positive"); break;
+        case 6: CB_REQUIRE(a > 0.0 && b > 0.0, "shape and scale must be positive"); break;
+        case 7: CB_REQUIRE(a > 0.0 && b > 0.0, "a and b must be positive"); break;
+    }
+    CB_CUDA(launch_dist_fill(kind, d_out, n, fa, fb, philox_keys_from_seed(seed), subsequence, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_randint(cb_ctx *c, void *d_out, int out_is_64, uint64_t n, int64_t low, int64_t high,
+                                 uint64_t seed, uint32_t subsequence) {
+    int rc = check_out(c, d_out, n);
+    if (rc) return rc;
+    CB_REQUIRE(high > low, "high must be greater than low");
+    const float divisor = (float)(1.0 / (double)(high - low));
+    CB_CUDA(launch_randint(d_out, out_is_64, n, divisor, (long long)low, philox_keys_from_seed(seed), subsequence,
+                           c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_gather(cb_ctx *c, void *d_out, const void *d_src, const int32_t *d_index, uint64_t n,
+                                int elem_bytes) {
+    int rc = check_out(c, d_out, n);
+    if (rc) return rc;
+    CB_REQUIRE(d_src != nullptr && d_index != nullptr, "NULL argument");
+    CB_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "element size must be 4 or 8 bytes");
+    CB_CUDA(launch_gather(d_out, d_src, d_index, n, elem_bytes, c->stream));
+    return CB_OK;
+}
+
+template <typename real>
+static int mvn(cb_ctx *c, real *d_out, uint64_t rows, int d, const real *h_chol, const real *h_mean, uint64_t seed,
+               uint32_t subsequence) {
+    int rc = check_out(c, d_out, rows * (uint64_t)d);
+    if (rc) return rc;
+    CB_REQUIRE(d >= 1 && d <= 64, "dimension must be in [1,64]");
+    CB_REQUIRE(h_chol != nullptr && h_mean != nullptr, "NULL argument");
+    const size_t bytes = sizeof(real) * ((size_t)d * d + d);
+    rc = ensure_scratch(c, bytes);
+    if (rc) return rc;
+    real *d_chol = (real *)c->scratch, *d_mean = d_chol + (size_t)d * d;
+    CB_CUDA(cudaMemcpyAsync(d_chol, h_chol, sizeof(real) * d * d, cudaMemcpyHostToDevice, c->stream));
+    CB_CUDA(cudaMemcpyAsync(d_mean, h_mean, sizeof(real) * d, cudaMemcpyHostToDevice, c->stream));
+    CB_CUDA((launch_random_fill<real, true>(d_out, rows * (uint64_t)d, philox_keys_from_seed(seed), subsequence,
+                                            c->stream)));
+    CB_CUDA(launch_mvn_transform<real>(d_out, rows, d, d_chol, d_mean, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));      // h_chol / h_mean are caller memory: done with them on return
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_multivariate_normal_f32(cb_ctx *c, float *d_out, uint64_t rows, int d, const float *h_chol,
+                                                 const float *h_mean, uint64_t seed, uint32_t subsequence) {
+    return mvn<float>(c, d_out, rows, d, h_chol, h_mean, seed, subsequence);
+}
+
+extern "C" CB_API int cb_multivariate_normal_f64(cb_ctx *c, double *d_out, uint64_t rows, int d, const double *h_chol,
+                                                 const double *h_mean, uint64_t seed, uint32_t subsequence) {
+    return mvn<double>(c, d_out, rows, d, h_chol, h_mean, seed, subsequence);
+}
+
 // ---------------------------------------------------------------- Heston: parity kernels
 
 static int check_heston(const cb_heston_params *p, uint64_t R, uint32_t N) {

@@ -81,6 +81,16 @@ template <typename real, bool NORMAL>
 cudaError_t launch_random_antithetic(real *d_out, uint64_t outer, uint64_t d_axis, uint64_t inner,
                                      const PhiloxKeys &k, uint32_t subseq, cudaStream_t s);
 
+// derived distributions (dist_kernels.cu)
+cudaError_t launch_dist_fill(int kind, float *d_out, uint64_t n, float a, float b, const PhiloxKeys &k,
+                             uint32_t subseq, cudaStream_t s);
+cudaError_t launch_randint(void *d_out, int out_is_64, uint64_t n, float divisor, long long low, const PhiloxKeys &k,
+                           uint32_t subseq, cudaStream_t s);
+cudaError_t launch_gather(void *d_out, const void *d_src, const int *d_idx, uint64_t n, int elem_bytes, cudaStream_t s);
+template <typename real>
+cudaError_t launch_mvn_transform(real *d_zx, uint64_t rows, int d, const real *d_chol, const real *d_mean,
+                                 cudaStream_t s);
+
 // Monte-Carlo pi
 cudaError_t launch_pi_count(uint64_t n, int antithetic, uint64_t draw_first, uint64_t draw_count,
                             const PhiloxKeys &k, uint32_t subseq, unsigned long long *d_inside,

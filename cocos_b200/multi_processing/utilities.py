@@ -1,12 +1,16 @@
-"""cocos/multi_processing/utilities.py: slice generators and argument normalisation."""
-import math
+"""Batch bookkeeping shared by the map-reduce front ends (reference: cocos/multi_processing/utilities.py)."""
+import enum
 import typing as tp
-from enum import Enum
+
+ResultType = tp.TypeVar('ResultType')
+ParameterTransferFunction = tp.Callable[..., tp.Tuple[tp.Sequence, tp.Dict[str, tp.Any]]]
+Span = tp.Tuple[int, int]
 
 
-class MultiprocessingPoolType(Enum):
-    """The reference offers loky or pathos process pools (utilities.py:23-40).  Here the
-    device pool is in-process (streams + NCCL) and the CPU pool is concurrent.futures."""
+class MultiprocessingPoolType(enum.Enum):
+    """The reference chooses between loky and pathos process pools (utilities.py:23-40).  Here the device pool
+    lives in one process (streams + NCCL) and the CPU pool is a concurrent.futures executor; the two reference
+    members are kept as names only."""
     LOKY = 1
     PATHOS = 2
     STREAMS = 3
@@ -17,51 +21,52 @@ class MultiprocessingPoolType(Enum):
         return MultiprocessingPoolType.STREAMS
 
 
-def generate_slices_with_batch_size(n: int, batch_size: int) -> tp.Tuple[tp.Tuple[int, int], ...]:
-    """Partition range(n) into consecutive (begin, end) ranges of length <= batch_size."""
+def _ceil_div(a: int, b: int) -> int:
+    return -(-a // b)
+
+
+def generate_slices_with_batch_size(n: int, batch_size: int) -> tp.Tuple[Span, ...]:
+    """Cut range(n) into consecutive (begin, end) spans no longer than ``batch_size`` (utilities.py:43-63)."""
     if batch_size <= 0:
         raise ValueError("batch_size must be positive")
-    return tuple((lo, min(lo + batch_size, n)) for lo in range(0, n, batch_size))
+    return tuple((begin, min(begin + batch_size, n)) for begin in range(0, n, batch_size))
 
 
-def generate_slices_with_number_of_batches(n: int, number_of_batches: int) -> tp.Tuple[tp.Tuple[int, int], ...]:
-    """Partition range(n) into ranges of length ceil(n/number_of_batches) (the last may be shorter)."""
-    return generate_slices_with_batch_size(n=n, batch_size=math.ceil(n / number_of_batches))
-
-
-ResultType = tp.TypeVar('ResultType')
-ParameterTransferFunction = tp.Callable[..., tp.Tuple[tp.Sequence, tp.Dict[str, tp.Any]]]
+def generate_slices_with_number_of_batches(n: int, number_of_batches: int) -> tp.Tuple[Span, ...]:
+    """Spans of length ceil(n / number_of_batches); the last one may be shorter (utilities.py:66-79)."""
+    return generate_slices_with_batch_size(n, _ceil_div(n, number_of_batches))
 
 
 def _extract_arguments_and_number_of_batches(
         args_list: tp.Optional[tp.Sequence[tp.Sequence]] = None,
         kwargs_list: tp.Optional[tp.Sequence[tp.Dict[str, tp.Any]]] = None,
         number_of_batches: tp.Optional[int] = None):
-    """utilities.py:88-106: derive the batch count and fill the missing argument lists."""
+    """Normalise the three optional batch descriptions of ``map_reduce`` / ``map_combine`` (utilities.py:88-106).
+
+    The batch count comes from ``number_of_batches``, else from ``args_list``, else from ``kwargs_list``; a missing
+    list becomes that many empty argument lists / dicts.  With nothing to go by the call is an error.
+    """
     if number_of_batches is None:
-        if args_list is not None:
-            number_of_batches = len(args_list)
-        elif kwargs_list is not None:
-            number_of_batches = len(kwargs_list)
-        else:
+        given = next((lst for lst in (args_list, kwargs_list) if lst is not None), None)
+        if given is None:
             raise ValueError('Number_of_batches must be defined if both args_list and kwargs_list are empty')
-    if args_list is None:
-        args_list = number_of_batches * [list()]
-    if kwargs_list is None:
-        kwargs_list = number_of_batches * [dict()]
-    return args_list, kwargs_list, number_of_batches
+        number_of_batches = len(given)
+    positional = args_list if args_list is not None else [[] for _ in range(number_of_batches)]
+    keyword = kwargs_list if kwargs_list is not None else [{} for _ in range(number_of_batches)]
+    return positional, keyword, number_of_batches
 
 
 def ordered_left_fold(indexed_results, reduction, initial_value):
-    """Reduce from the left in submission order (device_pool.py:246-251)."""
-    result = initial_value
+    """Fold (index, value) pairs from the left in INDEX order, whatever order they completed in
+    (device_pool.py:246-251)."""
+    accumulator = initial_value
     for _, value in sorted(indexed_results, key=lambda item: item[0]):
-        result = reduction(result, value)
-    return result
+        accumulator = reduction(accumulator, value)
+    return accumulator
 
 
-def shard_range(total: int, parts: int, index: int) -> tp.Tuple[int, int]:
-    """Contiguous shard ``index`` of ``parts``: (first, count) with ceil(total/parts) per shard."""
-    per = math.ceil(total / parts) if parts else 0
-    first = min(index * per, total)
-    return first, min(per, total - first)
+def shard_range(total: int, parts: int, index: int) -> Span:
+    """Contiguous shard ``index`` of ``parts``: (first, count) with ceil(total/parts) items per shard."""
+    per_shard = _ceil_div(total, parts) if parts else 0
+    first = min(index * per_shard, total)
+    return first, min(per_shard, total - first)

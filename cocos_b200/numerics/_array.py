@@ -18,11 +18,12 @@ def torch_dtype(dtype):
     import torch
     if _TORCH_DTYPES is None:
         _TORCH_DTYPES = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
-                         np.dtype(np.uint32): torch.uint32, np.dtype(np.int64): torch.int64}
+                         np.dtype(np.uint32): torch.uint32, np.dtype(np.int64): torch.int64,
+                         np.dtype(np.int32): torch.int32}
     try:
         return _TORCH_DTYPES[np.dtype(dtype)]
     except KeyError:
-        raise TypeError(f"dtype {dtype} is not supported on the device (float32 and float64 are)") from None
+        raise TypeError(f"dtype {dtype} is not supported on the device (float32/float64, int32/int64)") from None
 
 
 def empty_on(ctx, shape, dtype):

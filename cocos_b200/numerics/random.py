@@ -7,7 +7,9 @@ Same names and argument meaning as the reference for
   rand, randn                          random.py:127-153
   rand_with_dtype, randn_with_dtype    random.py:172-187
   randn_antithetic, rand_antithetic    random.py:190-245
-The derived distributions (random.py:252-531) are out of scope.
+and, one fused kernel each on the same generator,
+  randint, choice, uniform, exponential, standard_exponential, gamma, standard_gamma, chisquare, beta, wald,
+  normal, standard_normal, lognormal, logistic, multivariate_normal        random.py:252-531
 
 Generator: Philox4x32-10 (the reference's default engine, random.py:30-51), key =
 seed, one fresh 32-bit ``subsequence`` per kernel launch.  Host state is (seed,
@@ -191,3 +193,156 @@ def philox_words(n_blocks: int, first_index: int = 0, block: int = 0, subsequenc
     _lib.check(_lib.lib().cb_philox_words(ctx.handle, out.data_ptr, int(n_blocks), int(first_index), int(block), s,
                                           int(subsequence)))
     return out
+
+
+# ---------------------------------------------------------------------------
+# derived distributions (random.py:252-531): one fused kernel each, float32 like the reference
+# ---------------------------------------------------------------------------
+
+SIZE_TYPE = tp.Optional[tp.Union[int, tp.Sequence[int]]]
+_UNIFORM, _EXPONENTIAL, _NORMAL, _LOGNORMAL, _LOGISTIC, _WALD, _GAMMA, _BETA = range(8)
+
+
+def _count_and_shape(size: SIZE_TYPE) -> tp.Tuple[int, tp.Optional[tp.Tuple[int, ...]]]:
+    """Element count and final shape for the reference's ``size`` convention (_draw_and_reshape, random.py:306-326):
+    None -> one draw returned as a Python scalar, int -> 1-D, tuple/list -> that shape."""
+    if size is None or (not isinstance(size, (list, tuple)) and not size):
+        return 1, None
+    if isinstance(size, (int, np.integer)):
+        return int(size), (int(size),)
+    if isinstance(size, (list, tuple)):
+        return int(np.prod(size)), tuple(int(s) for s in size)
+    raise TypeError("size must be either of type int or tuple")
+
+
+def _finish(out: ndarray, shape, scalar_if_none: bool):
+    if shape is None:
+        return out.item() if scalar_if_none else out
+    return out.reshape(shape) if len(shape) != 1 else out
+
+
+def _distribution(kind: int, a: float, b: float, size: SIZE_TYPE):
+    n, shape = _count_and_shape(size)
+    ctx = current_context()
+    out = empty_on(ctx, (n,), np.float32)
+    _lib.check(_lib.lib().cb_random_distribution_f32(ctx.handle, out.data_ptr, n, kind, float(a), float(b), _state.seed,
+                                                     next_subsequence()))
+    return _finish(out, shape, scalar_if_none=(size is None))
+
+
+def uniform(low: float = 0.0, high: float = 1.0, size: SIZE_TYPE = None):
+    """Draw samples from a uniform distribution on [low, high)."""
+    if high < low:
+        raise ValueError("high must not be less than low")
+    return _distribution(_UNIFORM, low, high, size)
+
+
+def exponential(scale: float = 1.0, size: SIZE_TYPE = None, antithethic: bool = False):
+    return _distribution(_EXPONENTIAL, scale, 0.0, size)
+
+
+def standard_exponential(size: SIZE_TYPE = None):
+    return exponential(size=size)
+
+
+def normal(loc: float = 0.0, scale: float = 1.0, size: SIZE_TYPE = None):
+    return _distribution(_NORMAL, loc, scale, size)
+
+
+def standard_normal(size: SIZE_TYPE = None):
+    return _distribution(_NORMAL, 0.0, 1.0, size)
+
+
+def lognormal(mean: float = 0.0, sigma: float = 1.0, size: SIZE_TYPE = None):
+    return _distribution(_LOGNORMAL, mean, sigma, size)
+
+
+def logistic(loc: float = 0.0, scale: float = 1.0, size: SIZE_TYPE = None):
+    return _distribution(_LOGISTIC, loc, scale, size)
+
+
+def wald(mean: float, scale: float, size: SIZE_TYPE = None):
+    return _distribution(_WALD, mean, scale, size)
+
+
+def gamma(shape: float, scale: float = 1.0, size: SIZE_TYPE = None):
+    """Marsaglia-Tsang rejection sampling, one thread per value (the reference loops over array passes)."""
+    return _distribution(_GAMMA, shape, scale, size)
+
+
+def standard_gamma(shape: float, size: SIZE_TYPE = None):
+    return gamma(shape, size=size)
+
+
+def chisquare(df, size: SIZE_TYPE = None):
+    return gamma(df / 2.0, 2.0, size)
+
+
+def beta(a: float, b: float, size: SIZE_TYPE = None):
+    return _distribution(_BETA, a, b, size)
+
+
+def randint(low: int, high: tp.Optional[int] = None, size: tp.Optional[tp.Union[tp.Tuple[int, ...], int]] = None,
+            dtype: np.generic = np.int32) -> ndarray:
+    """Random integers in [low, high) (or [0, low) when ``high`` is omitted) of the given shape."""
+    if not high:
+        high, low = low, 0
+    if not size:
+        size = (1,)
+    elif isinstance(size, (int, np.integer)):
+        size = (int(size),)
+    n = int(np.prod(size))
+    ctx = current_context()
+    is64 = np.dtype(dtype) != np.dtype(np.int32)
+    if is64 and np.dtype(dtype) != np.dtype(np.int64):
+        raise TypeError("randint produces int32 or int64 on the device")
+    out = empty_on(ctx, (n,), np.int64 if is64 else np.int32)
+    _lib.check(_lib.lib().cb_randint(ctx.handle, out.data_ptr, int(is64), n, int(low), int(high), _state.seed,
+                                     next_subsequence()))
+    return out.reshape(tuple(int(s) for s in size))
+
+
+def choice(a: ndarray, size: tp.Optional[tp.Union[tp.Tuple[int, ...], int]] = None, replace: bool = True,
+           p=None) -> ndarray:
+    """Uniform draws with replacement from a device array."""
+    if p:
+        raise ValueError('p != None is not supported')
+    if not replace:
+        raise ValueError('replace=False is not supported')
+    if not isinstance(a, ndarray):
+        raise TypeError("a must be a cocos_b200 device array")
+    index = randint(0, a.size, size=size)
+    ctx = current_context()
+    flat = a.reshape(-1)
+    if not flat.tensor.is_contiguous():
+        raise ValueError("a must be contiguous")
+    out = empty_on(ctx, index.shape, a.dtype)
+    _lib.check(_lib.lib().cb_gather(ctx.handle, out.data_ptr, flat.data_ptr, index.data_ptr, index.size,
+                                    a.dtype.itemsize))
+    return out
+
+
+def multivariate_normal(mean, cov, size) -> ndarray:
+    """Rows of N(mean, cov): randn(n, d) @ cholesky(cov).T + mean, shape size + (d,).
+
+    (The reference computes ``z @ cholesky(cov).T`` and drops ``mean`` -- random.py:523-531; NumPy's semantics,
+    which its signature promises, are implemented here.)  The d x d factorisation is parameter preparation on the host.
+    """
+    mean = np.asarray(mean.to_numpy() if isinstance(mean, ndarray) else mean)
+    cov = np.asarray(cov.to_numpy() if isinstance(cov, ndarray) else cov)
+    d = len(mean)
+    if not isinstance(size, (list, tuple)):
+        size = [size]
+    if not cov.shape == (d, d):
+        raise ValueError('mean and cov must be a arrays with shapes (d, ) and (d, d) respectively')
+    if mean.dtype != cov.dtype:
+        raise ValueError('the dtypes of mean and cov mjust match')
+    sfx = _suffix(cov.dtype)
+    rows = int(np.prod(size))
+    chol = np.ascontiguousarray(np.linalg.cholesky(cov), dtype=cov.dtype)
+    mean = np.ascontiguousarray(mean, dtype=cov.dtype)
+    ctx = current_context()
+    out = empty_on(ctx, (rows, d), cov.dtype)
+    fn = getattr(_lib.lib(), f"cb_multivariate_normal_{sfx}")
+    _lib.check(fn(ctx.handle, out.data_ptr, rows, d, chol.ctypes.data, mean.ctypes.data, _state.seed, next_subsequence()))
+    return out.reshape(tuple(int(s) for s in size) + (d,))

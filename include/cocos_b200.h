@@ -100,6 +100,25 @@ CB_API int cb_rand_antithetic_f32(cb_ctx *ctx, float *d_out, const uint64_t *dim
 CB_API int cb_rand_antithetic_f64(cb_ctx *ctx, double *d_out, const uint64_t *dims, int ndim, int axis,
                            uint64_t seed, uint32_t subsequence);
 
+/* ---- derived distributions: cocos/numerics/random.py:252-531 ---------------
+ * kind: 0 uniform(a=low, b=high)   1 exponential(a=scale)        2 normal(a=loc, b=scale)
+ *       3 lognormal(a=mean, b=sigma) 4 logistic(a=loc, b=scale)  5 wald(a=mean, b=scale)
+ *       6 gamma(a=shape, b=scale) [chisquare(df) = gamma(df/2, 2)]   7 beta(a, b)
+ * float32 output, as in the reference (its derived distributions all start from rand(n)/randn(n)). */
+CB_API int cb_random_distribution_f32(cb_ctx *ctx, float *d_out, uint64_t n, int kind, double a, double b,
+                                      uint64_t seed, uint32_t subsequence);
+/* randint (random.py:252-287): integers in [low, high); int32 or int64 output */
+CB_API int cb_randint(cb_ctx *ctx, void *d_out, int out_is_64, uint64_t n, int64_t low, int64_t high,
+                      uint64_t seed, uint32_t subsequence);
+/* choice (random.py:290-303): out[i] = src[index[i]] for 4- or 8-byte elements */
+CB_API int cb_gather(cb_ctx *ctx, void *d_out, const void *d_src, const int32_t *d_index, uint64_t n, int elem_bytes);
+/* multivariate_normal (random.py:523-531): rows of randn(rows, d) times cholesky(cov)^T plus mean;
+ * h_chol is the LOWER Cholesky factor, row-major d x d (host), h_mean has d entries (host) */
+CB_API int cb_multivariate_normal_f32(cb_ctx *ctx, float *d_out, uint64_t rows, int d, const float *h_chol,
+                                      const float *h_mean, uint64_t seed, uint32_t subsequence);
+CB_API int cb_multivariate_normal_f64(cb_ctx *ctx, double *d_out, uint64_t rows, int d, const double *h_chol,
+                                      const double *h_mean, uint64_t seed, uint32_t subsequence);
+
 /* ---- Heston paths ---------------------------------------------------------
  * Parity kernels: simulate_heston_model (heston_utilities.py:58-96) with the
  * normals injected.  d_Z is [N-1][ceil(R/2)][2]; path i < ceil(R/2) uses +Z, path
