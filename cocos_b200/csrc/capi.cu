@@ -510,6 +510,52 @@ extern "C" CB_API int cb_multivariate_normal_f64(cb_ctx *c, double *d_out, uint6
     return mvn<double>(c, d_out, rows, d, h_chol, h_mean, seed, subsequence);
 }
 
+// ---------------------------------------------------------------- Gaussian KDE
+
+extern "C" CB_API int cb_kde_moments_f32(cb_ctx *c, const float *d_points, const float *d_weights_or_null, uint64_t n,
+                                         int d, double *h_out /* 1 + d + d*d */) {
+    CB_CTX(c);
+    CB_REQUIRE(d_points != nullptr && h_out != nullptr, "NULL argument");
+    CB_REQUIRE(d >= 1 && d <= 8, "dimension must be in [1,8]");
+    const size_t bytes = sizeof(double) * (1 + d + d * d);
+    int rc = ensure_scratch(c, bytes);
+    if (rc) return rc;
+    CB_CUDA(launch_kde_moments(d_points, d_weights_or_null, n, d, (double *)c->scratch, c->stream));
+    CB_CUDA(cudaMemcpyAsync(h_out, c->scratch, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_kde_whiten_f32(cb_ctx *c, const float *d_in, uint64_t n, int d, const float *h_matrix,
+                                        float *d_out) {
+    CB_CTX(c);
+    CB_REQUIRE(d_in != nullptr && d_out != nullptr && h_matrix != nullptr, "NULL argument");
+    CB_REQUIRE(d >= 1 && d <= 8, "dimension must be in [1,8]");
+    int rc = ensure_scratch(c, sizeof(float) * 64);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(c->scratch, h_matrix, sizeof(float) * d * d, cudaMemcpyHostToDevice, c->stream));
+    CB_CUDA(launch_kde_whiten(d_in, n, d, (const float *)c->scratch, d_out, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));      // h_matrix is caller memory
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_kde_evaluate_f32(cb_ctx *c, const float *d_wpoints, const float *d_weights_or_null,
+                                          uint64_t n, int d, const float *d_wxi, uint64_t m, double scale,
+                                          float *d_out) {
+    CB_CTX(c);
+    CB_REQUIRE(d_wpoints != nullptr && (d_wxi != nullptr || m == 0) && (d_out != nullptr || m == 0), "NULL argument");
+    CB_REQUIRE(d >= 1 && d <= 4, "the evaluation kernel supports 1 to 4 dimensions");
+    CB_REQUIRE(n >= 1, "empty dataset");
+    if (m == 0) return CB_OK;
+    int pj = 1;
+    const int chunks = kde_plan_chunks(n, m, c->sm_count, &pj);
+    int rc = ensure_scratch(c, sizeof(float) * (size_t)chunks * m);
+    if (rc) return rc;
+    CB_CUDA(launch_kde_evaluate(d_wpoints, d_weights_or_null, n, d, d_wxi, m, scale, (float *)c->scratch, chunks, pj,
+                                d_out, c->stream));
+    return CB_OK;
+}
+
 // ---------------------------------------------------------------- Heston: parity kernels
 
 static int check_heston(const cb_heston_params *p, uint64_t R, uint32_t N) {

@@ -91,6 +91,13 @@ template <typename real>
 cudaError_t launch_mvn_transform(real *d_zx, uint64_t rows, int d, const real *d_chol, const real *d_mean,
                                  cudaStream_t s);
 
+// Gaussian KDE (kde_kernels.cu)
+cudaError_t launch_kde_moments(const float *d_pts, const float *d_w, uint64_t n, int d, double *d_out, cudaStream_t s);
+cudaError_t launch_kde_whiten(const float *d_in, uint64_t n, int d, const float *d_W, float *d_out, cudaStream_t s);
+int kde_plan_chunks(uint64_t n, uint64_t m, int sm_count, int *pj_out);
+cudaError_t launch_kde_evaluate(const float *d_p, const float *d_w, uint64_t n, int d, const float *d_q, uint64_t m,
+                                double scale, float *d_partial, int chunks, int pj, float *d_out, cudaStream_t s);
+
 // Monte-Carlo pi
 cudaError_t launch_pi_count(uint64_t n, int antithetic, uint64_t draw_first, uint64_t draw_count,
                             const PhiloxKeys &k, uint32_t subseq, unsigned long long *d_inside,

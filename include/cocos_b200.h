@@ -119,6 +119,17 @@ CB_API int cb_multivariate_normal_f32(cb_ctx *ctx, float *d_out, uint64_t rows, 
 CB_API int cb_multivariate_normal_f64(cb_ctx *ctx, double *d_out, uint64_t rows, int d, const double *h_chol,
                                       const double *h_mean, uint64_t seed, uint32_t subsequence);
 
+/* ---- Gaussian KDE: cocos/scientific/kde.py:152-197 (evaluate), :1057-1170 (covariance, whitening) -------
+ * points are row-major (n, d) float32 on the device.
+ * cb_kde_moments_f32   h_out = [sum w, sum w x (d), sum w x x^T (d*d)] in double (weights NULL = all ones)
+ * cb_kde_whiten_f32    d_out = d_in @ M for a host d x d row-major matrix M (the whitening, pre-scaled)
+ * cb_kde_evaluate_f32  d_out[j] = scale * sum_i w_i * 2^(-|p_i - q_j|^2) for whitened, pre-scaled p (n,d), q (m,d) */
+CB_API int cb_kde_moments_f32(cb_ctx *ctx, const float *d_points, const float *d_weights_or_null, uint64_t n, int d,
+                              double *h_out);
+CB_API int cb_kde_whiten_f32(cb_ctx *ctx, const float *d_in, uint64_t n, int d, const float *h_matrix, float *d_out);
+CB_API int cb_kde_evaluate_f32(cb_ctx *ctx, const float *d_wpoints, const float *d_weights_or_null, uint64_t n, int d,
+                               const float *d_wxi, uint64_t m, double scale, float *d_out);
+
 /* ---- Heston paths ---------------------------------------------------------
  * Parity kernels: simulate_heston_model (heston_utilities.py:58-96) with the
  * normals injected.  d_Z is [N-1][ceil(R/2)][2]; path i < ceil(R/2) uses +Z, path
