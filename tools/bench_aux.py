@@ -121,6 +121,44 @@ def main():
         _lib.check(L.cb_pi_count_finish(ctx.handle, ctypes.byref(inside)))
         res[f"pi_1e9_{'antithetic' if anti else 'plain'}"] = {"ms": ms, "points_per_s": nn / ms * 1e3, "pi": 4 * inside.value / nn}
 
+    # ---- derived distributions (one fused kernel each) and the Gaussian KDE (MUFU.EX2 per pair)
+    mufu = min(peak(4), peak(1))
+    n_d = 1 << 28
+    buf = empty_on(ctx, (n_d,), np.float32)
+    for name, kind, a, b in (("uniform", 0, 2.0, 5.0), ("exponential", 1, 1.5, 0.0), ("normal", 2, 0.0, 1.0),
+                             ("lognormal", 3, 0.0, 0.5), ("logistic", 4, 5.0, 2.0), ("wald", 5, 1.0, 1.0),
+                             ("gamma_7.5", 6, 7.5, 1.0), ("gamma_0.5", 6, 0.5, 1.0), ("beta_2_5", 7, 2.0, 5.0)):
+        ms = timed(ctx, lambda: _lib.check(L.cb_random_distribution_f32(ctx.handle, buf.data_ptr, n_d, kind, a, b, 1, 0)), reps=3)
+        res["dist_" + name] = {"elements": n_d, "ms": ms, "elements_per_s": n_d / ms * 1e3, "GBs": n_d * 4 / ms / 1e6}
+    del buf
+    from cocos_b200.scientific.kde import gaussian_kde
+    from cocos_b200.numerics._array import ndarray as dev_array
+    rnd.seed(1)
+    x, _ = heston.simulate_heston_model(T=P["T"], N=101, R=2_000_000, mu=P["r"], kappa=P["kappa"], v_bar=P["v_bar"],
+                                        sigma_v=P["sigma_v"], rho=P["rho"], x0=P["x0"], v0=P["v0"])
+    ctx.sync()
+    prices = dev_array(x.tensor.exp(), ctx)
+    kde = gaussian_kde(prices)
+    for m in (1000, 100_000):
+        grid = np.linspace(0.3, 2.0, m)
+        xi = empty_on(ctx, (m, 1), np.float32)
+        w = np.ascontiguousarray((grid[:, None] * kde._matrix[0, 0]).astype(np.float32))
+        _lib.check(L.cb_memcpy_h2d(ctx.handle, xi.data_ptr, w.ctypes.data, w.nbytes))
+        out = empty_on(ctx, (m,), np.float32)
+        ms = timed(ctx, lambda: _lib.check(L.cb_kde_evaluate_f32(ctx.handle, kde._whitened.data_ptr, None, kde.n, 1, xi.data_ptr, m,
+                                                                  kde.normalization_constant / kde.n, out.data_ptr)), reps=3)
+        pairs = kde.n * m
+        res[f"kde_n2e6_m{m}"] = {"ms": ms, "pairs_per_s": pairs / ms * 1e3, "frac_mufu_peak": pairs / ms * 1e3 / mufu,
+                                 "integral": float(np.trapezoid(out.to_numpy(), grid))}
+
+    # ---- CPU pi baseline: the reference's estimate_pi semantics (NumPy, one core), 1e8 points in 20 batches
+    from oracle import heston_numpy as hn
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    pi_cpu = hn.estimate_pi(100_000_000, batches=20)
+    dt = time.perf_counter() - t0
+    res["pi_cpu_numpy_1core_1e8"] = {"seconds": dt, "points_per_s": 1e8 / dt, "pi": pi_cpu}
+
     for k, v in res.items():
         print(k, json.dumps(v))
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
