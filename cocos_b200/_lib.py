@@ -70,6 +70,8 @@ PROTOTYPES = {
                                            c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_heston_price_launch_f64": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,
                                            c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb_heston_price_conditional_launch_f32": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64,
+                                                       c_u32, c_u64, c_u64, c_void_p, c_void_p, c_void_p]),
     "cb_heston_price_finish": (c_int, [c_void_p, c_int, P(c_double), P(c_double)]),
     "cb_call_payoff_sums_f32": (c_int, [c_void_p, c_void_p, c_u64, P(c_double), c_int, P(c_double), P(c_double)]),
     "cb_call_payoff_sums_f64": (c_int, [c_void_p, c_void_p, c_u64, P(c_double), c_int, P(c_double), P(c_double)]),

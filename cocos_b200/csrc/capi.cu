@@ -758,6 +758,52 @@ extern "C" CB_API int cb_heston_price_launch_f64(cb_ctx *c, const cb_heston_para
                                        d_x, d_v, d_traj);
 }
 
+extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                            const double *h_strikes, int nK, uint64_t seed,
+                                                            uint32_t subsequence, uint64_t pair_first,
+                                                            uint64_t pair_count, cb_comm *comm, float *d_x, float *d_v) {
+    CB_CTX(c);
+    int rc = check_heston(p, R, N);
+    if (rc) return rc;
+    CB_REQUIRE(h_strikes != nullptr, "h_strikes is NULL");
+    CB_REQUIRE(nK >= 1 && nK <= CB_MAX_STRIKES, "nK must be in [1,%d]", CB_MAX_STRIKES);
+    CB_REQUIRE(p->sigma_v > 0.0, "the conditional scheme needs sigma_v > 0 (use the Euler kernel otherwise)");
+    const uint64_t H = (R + 1) / 2;
+    CB_REQUIRE(pair_first <= H && pair_count <= H - pair_first, "pair range outside [0,%llu)", (unsigned long long)H);
+    CB_REQUIRE((d_x == nullptr) == (d_v == nullptr), "d_x and d_v must both be given or both be NULL");
+    if (comm != nullptr) {
+        rc = need_nccl();
+        if (rc) return rc;
+    }
+    const FusedConsts<float> k = make_consts<float>(p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count);
+    if (pair_count > 0) {
+        const int threads = c->threads ? c->threads : 256;
+        int bps = 0;
+        CB_CUDA(conditional_occupancy(threads, nK > 1, &bps));
+        CB_REQUIRE(bps >= 1, "kernel does not fit");
+        if (c->blocks_per_sm > 0) bps = std::min(bps, c->blocks_per_sm);
+        const uint64_t items = (pair_count + threads - 1) / threads;
+        uint64_t blocks = std::min<uint64_t>(items, (uint64_t)c->sm_count * bps);
+        if (items > blocks) {                              // same wave-aware choice as choose_shape
+            double best = -1.0;
+            for (int b = bps; b >= std::max(1, (int)std::ceil(0.6 * bps)); --b) {
+                const uint64_t g = (uint64_t)c->sm_count * b, waves = (items + g - 1) / g;
+                const double eff = (double)items / ((double)waves * (double)g);
+                if (eff > best + 1e-9) { best = eff; blocks = g; }
+            }
+        }
+        const double dt = p->T / (double)(N - 1);
+        CB_CUDA(launch_heston_conditional(k, (float)p->sigma_v, (float)p->rho, (float)dt, threads, (int)blocks, c->ws,
+                                          d_x, d_v, c->stream));
+    } else {
+        CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));
+    }
+    if (comm != nullptr)
+        CB_NCCL(g_nccl.AllReduce(c->ws.result, c->ws.result, (size_t)2 * nK, ncclDouble, ncclSum, comm->comm,
+                                 c->stream));
+    return CB_OK;
+}
+
 extern "C" CB_API int cb_heston_price_finish(cb_ctx *c, int nK, double *h_sum, double *h_sumsq) {
     CB_CTX(c);
     CB_REQUIRE(nK >= 1 && nK <= CB_MAX_STRIKES, "nK must be in [1,%d]", CB_MAX_STRIKES);

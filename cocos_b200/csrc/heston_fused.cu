@@ -18,11 +18,11 @@
 //   x' = x - 0.5*dt*v + sqrt(v)*dB0          (mu*dt*(N-1) + x0 added once at the end)
 //   v' = max(a*v + b + sqrt(v)*w, eps_f32)
 #include "kernels.h"
+#include "payoff_reduce.cuh"
 
 namespace cb {
 
-constexpr int kMaxThreads = 256;
-constexpr int kMaxWarps = kMaxThreads / 32;
+constexpr int kMaxThreads = kFusedMaxThreads;
 
 // ---- per-type math ---------------------------------------------------------
 
@@ -151,13 +151,8 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
                         ((reinterpret_cast<uintptr_t>(traj) & (4 * sizeof(real) - 1)) == 0);
 
     __shared__ real s_strikes[kMaxStrikes];
-    if (MULTI) {
-        if (threadIdx.x < kMaxStrikes) s_strikes[threadIdx.x] = c.strikes[threadIdx.x < c.nK ? threadIdx.x : 0];
-        __syncthreads();
-    }
-
-    double acc_sum[MULTI ? 2 : 1] = {};
-    double acc_sq[MULTI ? 2 : 1] = {};
+    if (MULTI) stage_strikes(s_strikes, c.strikes, c.nK);
+    PayoffAccumulator<real, MULTI> acc;
     const real x_shift = c.x0 + (real)c.steps * c.mu_dt;
     const StepRegs<real> k(c);
     // 0x3F800000 in a register ptxas cannot constant-fold (steps < 2^31 always): keeps angle_float at one LOP3
@@ -271,101 +266,16 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
         for (int q = 0; q < PPT; ++q) {
             const real xT1 = x1[q] + x_shift, xT2 = x2[q] + x_shift;
             if (x_out != nullptr) {
-                if (active[q]) { x_out[local[q]] = xT1; v_out[local[q]] = v1[q] * k.inv_c1; }
-                if (paired[q]) { x_out[c.pair_count + local[q]] = xT2; v_out[c.pair_count + local[q]] = v2[q] * k.inv_c1; }
+                // u = c1*v back to v; a path sitting on the floor reports exactly eps_f32, as the reference's maximum() does
+                const real vT1 = v1[q] == k.floor_u ? c.floor_v : v1[q] * k.inv_c1;
+                const real vT2 = v2[q] == k.floor_u ? c.floor_v : v2[q] * k.inv_c1;
+                if (active[q]) { x_out[local[q]] = xT1; v_out[local[q]] = vT1; }
+                if (paired[q]) { x_out[c.pair_count + local[q]] = xT2; v_out[c.pair_count + local[q]] = vT2; }
             }
-            const real S1 = exp_real(xT1), S2 = exp_real(xT2);
-            if constexpr (!MULTI) {
-                const real K = c.strikes[0];
-                const real p1 = active[q] ? fmax(S1 - K, (real)0) : (real)0;
-                const real p2 = paired[q] ? fmax(S2 - K, (real)0) : (real)0;
-                const double tot = (double)(p1 + p2);
-                const double unit = paired[q] ? 0.5 * tot : tot;
-                acc_sum[0] += tot;
-                acc_sq[0] = fma(unit, unit, acc_sq[0]);
-            } else {
-                // lane-transposed sweep: lane l keeps strikes l and l+32 for the whole warp
-                const real m1 = active[q] ? (real)1 : (real)0;
-                const real m2 = paired[q] ? (real)1 : (real)0;
-                for (int src = 0; src < 32; ++src) {
-                    const real s1 = __shfl_sync(0xffffffffu, S1, src);
-                    const real s2 = __shfl_sync(0xffffffffu, S2, src);
-                    const real g1 = __shfl_sync(0xffffffffu, m1, src);
-                    const real g2 = __shfl_sync(0xffffffffu, m2, src);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const real K = s_strikes[lane + 32 * h];
-                        const real p1 = g1 * fmax(s1 - K, (real)0);
-                        const real p2 = g2 * fmax(s2 - K, (real)0);
-                        const double tot = (double)(p1 + p2);
-                        const double unit = tot * (0.5 + 0.5 * (double)(g1 - g2));   // 0.5*tot if paired, tot if single
-                        acc_sum[h] += tot;
-                        acc_sq[h] = fma(unit, unit, acc_sq[h]);
-                    }
-                }
-            }
+            acc.add(exp_real(xT1), exp_real(xT2), active[q], paired[q], c.strikes[0], s_strikes, lane);
         }
     }
-
-    // ---- block reduction -> per-block partials -> last block folds them in a fixed order ----
-    const int nacc = 2 * c.nK;
-    __shared__ double s_acc[kMaxWarps][kMaxAcc];
-    __shared__ bool s_last;
-    const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
-    if (!MULTI) {
-        const double a = warp_sum(acc_sum[0]), b = warp_sum(acc_sq[0]);
-        if (lane == 0) { s_acc[warp][0] = a; s_acc[warp][1] = b; }
-    } else {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int k = lane + 32 * h;
-            if (k < c.nK) { s_acc[warp][k] = acc_sum[h]; s_acc[warp][c.nK + k] = acc_sq[h]; }
-        }
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < nacc) {
-        double t = 0.0;
-        for (int w = 0; w < nwarps; ++w) t += s_acc[w][threadIdx.x];
-        ws.partials[(size_t)blockIdx.x * kMaxAcc + threadIdx.x] = t;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(ws.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int nb = gridDim.x;
-    if (nacc <= 2) {
-        double t[2] = {0.0, 0.0};
-        for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-            t[0] += __ldcg(ws.partials + (size_t)b * kMaxAcc);
-            t[1] += __ldcg(ws.partials + (size_t)b * kMaxAcc + 1);
-        }
-        t[0] = warp_sum(t[0]);
-        t[1] = warp_sum(t[1]);
-        __syncthreads();
-        if (lane == 0) { s_acc[warp][0] = t[0]; s_acc[warp][1] = t[1]; }
-        __syncthreads();
-        if (threadIdx.x < 2) {
-            double r = 0.0;
-            for (int w = 0; w < nwarps; ++w) r += s_acc[w][threadIdx.x];
-            ws.result[threadIdx.x] = r;
-        }
-    } else {
-        for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-            int b = 0;
-            for (; b + 3 < nb; b += 4) {
-                t0 += __ldcg(ws.partials + (size_t)(b + 0) * kMaxAcc + a);
-                t1 += __ldcg(ws.partials + (size_t)(b + 1) * kMaxAcc + a);
-                t2 += __ldcg(ws.partials + (size_t)(b + 2) * kMaxAcc + a);
-                t3 += __ldcg(ws.partials + (size_t)(b + 3) * kMaxAcc + a);
-            }
-            for (; b < nb; ++b) t0 += __ldcg(ws.partials + (size_t)b * kMaxAcc + a);
-            ws.result[a] = (t0 + t1) + (t2 + t3);
-        }
-    }
-    if (threadIdx.x == 0) *ws.ticket = 0u;   // ready for the next launch on this stream
+    acc.publish(c.nK, ws);
 }
 
 // ---- host side ---------------------------------------------------------------

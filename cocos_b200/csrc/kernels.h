@@ -55,6 +55,11 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
 template <typename real>
 cudaError_t fused_occupancy(int threads, int pairs_per_thread, bool multi, int variant, int *blocks_per_sm, int *regs);
 
+// conditional-Gaussian scheme (heston_conditional.cu)
+cudaError_t launch_heston_conditional(const FusedConsts<float> &c, float sigma_v, float rho, float dt, int threads,
+                                      int blocks, ReduceWorkspace ws, float *d_x, float *d_v, cudaStream_t stream);
+cudaError_t conditional_occupancy(int threads, bool multi, int *blocks_per_sm);
+
 // parity kernels (reference operation order, injected normals)
 struct InjectedConsts32 {
     float dt, root_dt, m0, m1, mu, kappa, v_bar, sigma_v, x0, v0;

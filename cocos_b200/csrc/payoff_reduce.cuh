@@ -1,0 +1,130 @@
+// Call-payoff accumulation and the grid-wide reduction shared by the fused Heston kernels.
+//
+//   compute_option_price_from_simulated_paths     examples/stochastic_volatility/heston_utilities.py:99-119
+//   host left fold of ComputeDevicePool           cocos/multi_processing/device_pool.py:246-251
+//
+// Per thread: f64 accumulators of sum(payoff) and sum(antithetic-unit average ^2) -- one strike, or (MULTI) the
+// lane-transposed sweep in which lane l keeps strikes l and l+32 for its whole warp and terminal prices are
+// broadcast by shuffle.  Per block: warp shuffles / shared memory -> partials[block].  The last block to arrive
+// (atomic ticket) folds the partials in block order into ws.result, so a launch is bit-reproducible, and resets
+// the ticket for the next launch on the stream.  ws.result is also the NCCL send/receive buffer.
+#pragma once
+#include "kernels.h"
+
+namespace cb {
+
+constexpr int kFusedMaxThreads = 256;
+constexpr int kFusedMaxWarps = kFusedMaxThreads / 32;
+
+template <typename real, bool MULTI>
+struct PayoffAccumulator {
+    double sum[MULTI ? 2 : 1] = {};
+    double sq[MULTI ? 2 : 1] = {};
+
+    // S1, S2: terminal prices of a pair; active: the pair exists; paired: its partner exists.
+    // Every lane of the warp must call this together (MULTI shuffles).
+    __device__ __forceinline__ void add(real S1, real S2, bool active, bool paired, real K0, const real *s_strikes,
+                                        unsigned lane) {
+        if constexpr (!MULTI) {
+            const real p1 = active ? fmax(S1 - K0, (real)0) : (real)0;
+            const real p2 = paired ? fmax(S2 - K0, (real)0) : (real)0;
+            const double tot = (double)(p1 + p2);
+            const double unit = paired ? 0.5 * tot : tot;
+            sum[0] += tot;
+            sq[0] = fma(unit, unit, sq[0]);
+        } else {
+            const real m1 = active ? (real)1 : (real)0;
+            const real m2 = paired ? (real)1 : (real)0;
+            for (int src = 0; src < 32; ++src) {
+                const real s1 = __shfl_sync(0xffffffffu, S1, src);
+                const real s2 = __shfl_sync(0xffffffffu, S2, src);
+                const real g1 = __shfl_sync(0xffffffffu, m1, src);
+                const real g2 = __shfl_sync(0xffffffffu, m2, src);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const real K = s_strikes[lane + 32 * h];
+                    const real p1 = g1 * fmax(s1 - K, (real)0);
+                    const real p2 = g2 * fmax(s2 - K, (real)0);
+                    const double tot = (double)(p1 + p2);
+                    const double unit = tot * (0.5 + 0.5 * (double)(g1 - g2));   // 0.5*tot if paired, tot if single
+                    sum[h] += tot;
+                    sq[h] = fma(unit, unit, sq[h]);
+                }
+            }
+        }
+    }
+
+    // Block reduction -> per-block partials -> the last block folds them in a fixed order.  Call once per thread,
+    // by every thread of the block.
+    __device__ __forceinline__ void publish(int nK, ReduceWorkspace ws) const {
+        const int nacc = 2 * nK;
+        __shared__ double s_acc[kFusedMaxWarps][kMaxAcc];
+        __shared__ bool s_last;
+        const unsigned lane = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+        if constexpr (!MULTI) {
+            const double a = warp_sum(sum[0]), b = warp_sum(sq[0]);
+            if (lane == 0) { s_acc[warp][0] = a; s_acc[warp][1] = b; }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = lane + 32 * h;
+                if (k < nK) { s_acc[warp][k] = sum[h]; s_acc[warp][nK + k] = sq[h]; }
+            }
+        }
+        __syncthreads();
+        for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+            double t = 0.0;
+            for (int w = 0; w < nwarps; ++w) t += s_acc[w][a];
+            ws.partials[(size_t)blockIdx.x * kMaxAcc + a] = t;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(ws.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const int nb = gridDim.x;
+        if (nacc <= 2) {
+            double t[2] = {0.0, 0.0};
+            for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+                t[0] += __ldcg(ws.partials + (size_t)b * kMaxAcc);
+                t[1] += __ldcg(ws.partials + (size_t)b * kMaxAcc + 1);
+            }
+            t[0] = warp_sum(t[0]);
+            t[1] = warp_sum(t[1]);
+            __syncthreads();
+            if (lane == 0) { s_acc[warp][0] = t[0]; s_acc[warp][1] = t[1]; }
+            __syncthreads();
+            if (threadIdx.x < 2) {
+                double r = 0.0;
+                for (int w = 0; w < nwarps; ++w) r += s_acc[w][threadIdx.x];
+                ws.result[threadIdx.x] = r;
+            }
+        } else {
+            for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                int b = 0;
+                for (; b + 3 < nb; b += 4) {
+                    t0 += __ldcg(ws.partials + (size_t)(b + 0) * kMaxAcc + a);
+                    t1 += __ldcg(ws.partials + (size_t)(b + 1) * kMaxAcc + a);
+                    t2 += __ldcg(ws.partials + (size_t)(b + 2) * kMaxAcc + a);
+                    t3 += __ldcg(ws.partials + (size_t)(b + 3) * kMaxAcc + a);
+                }
+                for (; b < nb; ++b) t0 += __ldcg(ws.partials + (size_t)b * kMaxAcc + a);
+                ws.result[a] = (t0 + t1) + (t2 + t3);
+            }
+        }
+        if (threadIdx.x == 0) *ws.ticket = 0u;   // ready for the next launch on this stream
+    }
+};
+
+// strikes of the sweep in shared memory (lane-indexed reads); entries past nK repeat strike 0
+template <typename real>
+__device__ __forceinline__ void stage_strikes(real *s_strikes, const real *strikes, int nK) {
+    if (threadIdx.x < kMaxStrikes) s_strikes[threadIdx.x] = strikes[threadIdx.x < nK ? threadIdx.x : 0];
+    for (int t = threadIdx.x + blockDim.x; t < kMaxStrikes; t += blockDim.x) s_strikes[t] = strikes[t < nK ? t : 0];
+    __syncthreads();
+}
+
+}  // namespace cb

@@ -58,10 +58,15 @@ class ShardedPricer:
             self.comm = handle
 
     def launch(self, params: "_lib.HestonParams", R: int, nT: int, strikes, seed: int, subsequence: int,
-               dtype_suffix: str = "f32"):
+               dtype_suffix: str = "f32", scheme: str = "euler"):
         """Asynchronous: this rank's shard of the simulation, then the allreduce, on one stream."""
         k_arr, nK = _lib.strikes_array(strikes)
         first, count = pair_shard(R, self.world_size, self.rank)
+        if scheme == "conditional":
+            _lib.check(_lib.lib().cb_heston_price_conditional_launch_f32(
+                self.ctx.handle, ctypes.byref(params), int(R), int(nT), k_arr, nK, int(seed), int(subsequence), first,
+                count, self.comm, None, None))
+            return nK
         fn = getattr(_lib.lib(), f"cb_heston_price_launch_{dtype_suffix}")
         _lib.check(fn(self.ctx.handle, ctypes.byref(params), int(R), int(nT), k_arr, nK, int(seed), int(subsequence),
                       first, count, self.comm, None, None, None))

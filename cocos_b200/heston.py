@@ -110,20 +110,37 @@ def _price_from_sums(r, T, R, sums, sumsq):
     return price, se
 
 
+SCHEMES = ("euler", "conditional")
+
+
 def heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, strikes, dtype=np.float32,
-                       compute_device_pool: tp.Optional[ComputeDevicePool] = None):
-    """One fused launch per device: undiscounted payoff sums for every strike."""
+                       compute_device_pool: tp.Optional[ComputeDevicePool] = None, scheme: str = "euler"):
+    """One fused launch per device: undiscounted payoff sums for every strike.
+
+    ``scheme="euler"`` steps log price and variance together, as the reference does.  ``scheme="conditional"``
+    (float32, opt-in) samples the log price conditionally on the variance path: the same law of terminal prices and
+    of antithetic pairs with half the normals (csrc/heston_conditional.cu), ~1.6x faster.
+    """
+    if scheme not in SCHEMES:
+        raise ValueError(f"scheme must be one of {SCHEMES}")
     R, nT = int(R), int(nT)
     p = _params(T, r, kappa, v_bar, sigma_v, rho, x0, v0)
     seed, sub = _random.get_seed(), _random.next_subsequence()
     sfx = _suffix(dtype)
+    if scheme == "conditional" and sfx != "f32":
+        raise TypeError("the conditional scheme is float32 only")
     if compute_device_pool is not None:
-        return compute_device_pool.heston_sums(p, R, nT, strikes, seed, sub, sfx)
+        return compute_device_pool.heston_sums(p, R, nT, strikes, seed, sub, sfx, scheme=scheme)
     ctx = current_context()
     L = _lib.lib()
     k_arr, nK = _lib.strikes_array(strikes)
-    launch = getattr(L, f"cb_heston_price_launch_{sfx}")
-    _lib.check(launch(ctx.handle, ctypes.byref(p), R, nT, k_arr, nK, seed, sub, 0, (R + 1) // 2, None, None, None, None))
+    if scheme == "conditional":
+        _lib.check(L.cb_heston_price_conditional_launch_f32(ctx.handle, ctypes.byref(p), R, nT, k_arr, nK, seed, sub, 0,
+                                                            (R + 1) // 2, None, None, None))
+    else:
+        launch = getattr(L, f"cb_heston_price_launch_{sfx}")
+        _lib.check(launch(ctx.handle, ctypes.byref(p), R, nT, k_arr, nK, seed, sub, 0, (R + 1) // 2, None, None, None,
+                          None))
     sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
     _lib.check(L.cb_heston_price_finish(ctx.handle, nK, sums, sumsq))
     return list(sums), list(sumsq)
@@ -132,27 +149,29 @@ def heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, strikes,
 def simulate_and_compute_option_price(
         x0: float, v0: float, r: float, rho: float, sigma_v: float, kappa: float, v_bar: float, T: float, K: float,
         nT: int, R: int, numerical_package_bundle: tp.Optional[tp.Type[NumericalPackageBundle]] = B200Bundle,
-        verbose: bool = False) -> float:
+        verbose: bool = False, scheme: str = "euler") -> float:
     """Price a European call under Heston by Monte Carlo: the fused kernel, one launch."""
     _require_b200(numerical_package_bundle)
     if verbose:
         print(f'computing on device={ComputeDeviceManager.get_current_compute_device_id()}')
-    sums, _ = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, [K])
+    sums, _ = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, [K], scheme=scheme)
     return float(math.exp(-r * T) * sums[0] / int(R))
 
 
 def price_with_standard_error(x0, v0, r, rho, sigma_v, kappa, v_bar, T, K, nT, R, dtype=np.float32,
-                              compute_device_pool: tp.Optional[ComputeDevicePool] = None) -> tp.Tuple[float, float]:
-    sums, sumsq = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, [K], dtype, compute_device_pool)
+                              compute_device_pool: tp.Optional[ComputeDevicePool] = None,
+                              scheme: str = "euler") -> tp.Tuple[float, float]:
+    sums, sumsq = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, [K], dtype, compute_device_pool,
+                                     scheme)
     price, se = _price_from_sums(r, T, int(R), sums, sumsq)
     return float(price[0]), float(se[0])
 
 
 def price_strike_sweep(x0, v0, r, rho, sigma_v, kappa, v_bar, T, strikes, nT, R, dtype=np.float64,
-                       compute_device_pool: tp.Optional[ComputeDevicePool] = None):
+                       compute_device_pool: tp.Optional[ComputeDevicePool] = None, scheme: str = "euler"):
     """Prices and standard errors for up to 64 strikes sharing one set of paths (BASELINE config 5)."""
     sums, sumsq = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, strikes, dtype,
-                                     compute_device_pool)
+                                     compute_device_pool, scheme)
     return _price_from_sums(r, T, int(R), sums, sumsq)
 
 

@@ -156,10 +156,16 @@ class ComputeDevicePool:
         return self._comms
 
     def heston_sums(self, params: "_lib.HestonParams", R: int, N: int, strikes, seed: int, subsequence: int,
-                    dtype_suffix: str = "f32") -> tp.Tuple[tp.List[float], tp.List[float]]:
+                    dtype_suffix: str = "f32", scheme: str = "euler") -> tp.Tuple[tp.List[float], tp.List[float]]:
         """Shard ceil(R/2) antithetic pairs over the pool; one NCCL allreduce; returns (sums, sumsq)."""
         L = _lib.lib()
-        launch = getattr(L, f"cb_heston_price_launch_{dtype_suffix}")
+        if scheme == "conditional":
+            raw = L.cb_heston_price_conditional_launch_f32
+
+            def launch(ctx_h, p, R_, N_, k, nk, sd, sub, first, count, comm, dx, dv, dtraj):
+                return raw(ctx_h, p, R_, N_, k, nk, sd, sub, first, count, comm, dx, dv)
+        else:
+            launch = getattr(L, f"cb_heston_price_launch_{dtype_suffix}")
         k_arr, nK = _lib.strikes_array(strikes)
         pairs = (R + 1) // 2
         G = self.number_of_devices

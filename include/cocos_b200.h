@@ -173,6 +173,13 @@ CB_API int cb_heston_price_launch_f64(cb_ctx *ctx, const cb_heston_params *p, ui
                                uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
                                double *d_x, double *d_v, double *d_traj);
 CB_API int cb_heston_price_finish(cb_ctx *ctx, int nK, double *h_sum, double *h_sumsq);
+/* Opt-in scheme with the same law of terminal prices (and of antithetic pairs) as the Euler kernel above but half
+ * the normals: the log price is sampled conditionally on the variance path (csrc/heston_conditional.cu).  Statistical
+ * mode only (no trajectory); results are collected with cb_heston_price_finish. */
+CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                  const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                                  uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                                                  float *d_x, float *d_v);
 
 /* compute_option_price_from_simulated_paths (heston_utilities.py:99-119) on a
  * device array of terminal log prices in the reference layout. */

@@ -247,3 +247,53 @@ def payoff_sums(x_T, strikes):
         sums.append(pay.sum())
         sumsq.append((unit * unit).sum())
     return np.array(sums), np.array(sumsq)
+
+
+# --------------------------------------------------------------------------
+# model of the conditional-Gaussian kernel (cocos_b200/csrc/heston_conditional.cu)
+# --------------------------------------------------------------------------
+
+def conditional_model(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, seed, subsequence, pair_offset=0):
+    """Terminal (x, v) of the opt-in conditional scheme from the same Philox words, in float64.
+
+    Law-equivalent to heston_terminal (the Euler scheme of heston_utilities.py:79-91): the variance recursion is
+    driven by w = rho z0 + rho' z1 only, the orthogonal Gaussian part of each pair is drawn once at the end from
+    block 0xFFFFFFFF.  One Philox block feeds six steps: draw j (0..2) gives (r cos, r sin) for steps 6b+2j, 6b+2j+1.
+    """
+    steps = nT - 1
+    dt = T / steps
+    H, F = (R + 1) // 2, R // 2
+    idx = np.arange(H, dtype=np.uint64) + np.uint64(pair_offset)
+    eps = float(F32_EPS)
+    v1 = np.full(H, v0, dtype=np.float64)
+    v2 = v1.copy()
+    A = np.zeros(H); B = np.zeros(H); C = np.zeros(H); P1 = np.zeros(H); P2 = np.zeros(H)
+    a, b = 1.0 - kappa * dt, kappa * v_bar * dt
+    scale = sigma_v * math.sqrt(dt)
+    t = 0
+    blk = 0
+    while t < steps:
+        w = px.philox_block(idx, blk, subsequence, seed)
+        for j in range(3):
+            za, zb = px.box_muller_f64_from_fields(w[j] >> np.uint32(9), px.angle19(w[j], w[3], j))
+            for z in (za, zb):
+                if t >= steps:
+                    break
+                ws = scale * z
+                s1, s2 = np.sqrt(v1), np.sqrt(v2)
+                A += v1; B += v2; C += s1 * s2; P1 += s1 * ws; P2 += s2 * ws
+                v1 = np.maximum(a * v1 + b + s1 * ws, eps)
+                v2 = np.maximum(a * v2 + b - s2 * ws, eps)
+                t += 1
+        blk += 1
+    fin = px.philox_block(idx, 0xFFFFFFFF, subsequence, seed)
+    z1, z2 = px.box_muller_f64(fin[0], fin[1])
+    rootA = np.sqrt(A)
+    G1 = rootA * z1
+    cross = np.where(A > 0, C / np.where(A > 0, rootA, 1.0), 0.0)
+    G2 = -cross * z1 + np.sqrt(np.maximum(B - cross * cross, 0.0)) * z2
+    base = x0 + steps * (r * dt)
+    orth = math.sqrt(max(1.0 - rho * rho, 0.0)) * math.sqrt(dt)
+    xa = base - 0.5 * dt * A + (rho / sigma_v) * P1 + orth * G1
+    xb = base - 0.5 * dt * B - (rho / sigma_v) * P2 + orth * G2
+    return np.concatenate([xa, xb[:F]]), np.concatenate([v1, v2[:F]])
