@@ -227,6 +227,18 @@ def run_b200(args):
     sums, sumsq = pricer.finish(nK)
     price, se = heston._price_from_sums(PARAMS["r"], PARAMS["T"], R, sums, sumsq)
 
+    # ---- informational: the opt-in conditional-Gaussian scheme (same law of terminal prices, half the normals);
+    #      NOT the headline: `value` above is the reference's step-by-step Euler scheme
+    cond_ms = 0.0
+    for i in range(3 + 5):
+        pricer.ctx.timer_start()
+        nK = pricer.launch(p, R, N_T, [PARAMS["K"]], args.seed, 1_000_000 + i, scheme="conditional")
+        ms = pricer.ctx.timer_stop()
+        if i >= 3:
+            cond_ms += ms
+    csums, csumsq = pricer.finish(nK)
+    cond_price, cond_se = heston._price_from_sums(PARAMS["r"], PARAMS["T"], R, csums, csumsq)
+
     # ---- end to end: the public entry point, host scalars in, host float out, wall clock
     barrier()
     t0 = time.perf_counter()
@@ -244,9 +256,9 @@ def run_b200(args):
 
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor([dev_ms, e2e_s, cond_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
+        dev_ms, e2e_s, cond_ms = float(t[0]), float(t[1]), float(t[2])
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -295,6 +307,10 @@ def run_b200(args):
                          "fp32_frac": per_gpu / fp32_roof, "fp32_peak_tflops": 2 * ffma_peak / 1e12,
                          "roof_path_steps_per_s": min(sfu_roof, fp32_roof)},
             "clocks": clocks,
+            "extras": {"conditional_scheme": {"value": R * (N_T - 1) * 5 / (cond_ms * 1e-3), "unit": UNIT,
+                                              "price": float(cond_price[0]), "price_se": float(cond_se[0]),
+                                              "note": "opt-in scheme='conditional': log price sampled conditionally on "
+                                                      "the variance path, same law as the Euler scheme, 5 launches"}},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
