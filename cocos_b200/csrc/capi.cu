@@ -667,8 +667,9 @@ static FusedConsts<real> make_consts(const cb_heston_params *p, uint64_t R, uint
 // last wave is fullest; every thread then runs the same number of iterations.
 template <typename real>
 static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, LaunchShape *s) {
-    const int threads = c->threads ? c->threads : 256;
-    const int ppt = traj ? 4 : (c->ppt ? c->ppt : 1);
+    // defaults from the tools/tune_fused.py sweeps: float 256 threads x 1 pair, double 128 threads x 2 pairs
+    const int threads = c->threads ? c->threads : (sizeof(real) == 8 ? 128 : 256);
+    const int ppt = traj ? 4 : (c->ppt ? c->ppt : (sizeof(real) == 8 ? 2 : 1));
     const int variant = (sizeof(real) == 4 && !multi && !traj) ? c->variant : 0;
     const auto key = std::make_tuple((int)(sizeof(real) == 8), traj ? -4 : ppt, (int)multi, threads, variant);
     auto it = c->occ_cache.find(key);

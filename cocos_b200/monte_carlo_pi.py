@@ -14,8 +14,10 @@ from .device import current_context
 from .numerics import random as _random
 
 
-def count_inside(n: int, antithetic: bool = False) -> int:
-    """Number of the n points that fall inside the quarter circle."""
+def count_inside(n: int, antithetic: bool = False, compute_device_pool=None) -> int:
+    """Number of the n points that fall inside the quarter circle (sharded over a pool's GPUs when given)."""
+    if compute_device_pool is not None:
+        return compute_device_pool.pi_inside(int(n), _random.get_seed(), _random.next_subsequence(), antithetic)
     ctx = current_context()
     L = _lib.lib()
     ndraw = (n + 1) // 2 if antithetic else n
@@ -26,12 +28,17 @@ def count_inside(n: int, antithetic: bool = False) -> int:
     return inside.value
 
 
-def estimate_pi(n: int, batches: int = 1, gpu: bool = True, antithetic: bool = False) -> float:
-    """4 * (fraction of points inside the quarter circle), averaged over ``batches`` batches of ceil(n/batches)."""
+def estimate_pi(n: int, batches: int = 1, gpu: bool = True, antithetic: bool = False,
+                compute_device_pool=None) -> float:
+    """4 * (fraction of points inside the quarter circle), averaged over ``batches`` batches of ceil(n/batches).
+
+    With ``compute_device_pool`` every batch is sharded over the pool's GPUs (disjoint draw ranges, one NCCL
+    allreduce of the count) instead of the reference's map_reduce of whole batches
+    (monte_carlo_pi_multi_gpu_example.py:185-188); the estimate does not depend on the number of GPUs."""
     if not gpu:
         raise NotImplementedError("cocos_b200 has no CPU branch (see oracle/ for the NumPy restatement)")
     n_per_batch = math.ceil(n / batches)
     pi = 0.0
     for _ in range(batches):
-        pi += 4.0 * count_inside(n_per_batch, antithetic) / n_per_batch
+        pi += 4.0 * count_inside(n_per_batch, antithetic, compute_device_pool) / n_per_batch
     return pi / batches

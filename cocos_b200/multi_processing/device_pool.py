@@ -186,6 +186,27 @@ class ComputeDevicePool:
             _lib.check(L.cb_heston_price_finish(ctx.handle, nK, sums, sumsq))
         return list(sums), list(sumsq)
 
+    def pi_inside(self, n: int, seed: int, subsequence: int, antithetic: bool) -> int:
+        """Shard the draws of a Monte-Carlo pi estimate over the pool; one NCCL allreduce of the inside count."""
+        L = _lib.lib()
+        ndraw = (n + 1) // 2 if antithetic else n
+        G = self.number_of_devices
+        comms = self._communicators()
+        if comms is not None:
+            _lib.check(L.cb_group_start())
+        try:
+            for g, ctx in enumerate(self._contexts):
+                first, count = shard_range(ndraw, G, g)
+                _lib.check(L.cb_pi_count_launch(ctx.handle, int(n), seed, subsequence, int(bool(antithetic)), first, count,
+                                                comms[g] if comms is not None else None))
+        finally:
+            if comms is not None:
+                _lib.check(L.cb_group_end())
+        inside = ctypes.c_uint64(0)
+        for ctx in reversed(self._contexts):
+            _lib.check(L.cb_pi_count_finish(ctx.handle, ctypes.byref(inside)))
+        return inside.value
+
     def close(self):
         if self._comms is not None:
             for c in self._comms:

@@ -141,6 +141,15 @@ def test_trajectory_mode(ctx, P):
     assert np.array_equal(tr[-1][:R], xr[:R])
 
 
+def test_trajectory_mode_f64(ctx, P):
+    R, N = 4_000, 25
+    s, q, x, v, traj = fused(ctx, P, R, N, [0.95], seed=6, sub=3, dtype=np.float64, outputs=True, traj=True)
+    assert traj.dtype == np.float64 and traj.shape == (N, R)
+    assert np.array_equal(traj[-1], x[:R]) and np.all(traj[0] == P["x0"])
+    x32 = fused(ctx, P, R, N, [0.95], seed=6, sub=3, dtype=np.float32, outputs=True)[2]
+    np.testing.assert_allclose(x[:R], x32[:R], atol=2e-5)           # same stream, float64 vs float32 state
+
+
 @pytest.mark.parametrize("nT,R", [(101, 4_000_000), (253, 2_000_000), (501, 2_000_000), (1001, 1_000_000)])
 def test_price_within_3se_of_reference(gpu_device, golden_values, ref_params, nT, R):
     """Correctness check (2): in-kernel RNG price vs the reference's NumPy price, 3 combined SE."""

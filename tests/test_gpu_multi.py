@@ -70,6 +70,23 @@ def test_reference_multi_gpu_entry_point(gpu_device, golden_values, ref_params):
 
 
 @needs2
+def test_pi_sharded_over_pool(gpu_device):
+    from cocos_b200 import monte_carlo_pi as mcp
+    from cocos_b200.multi_processing import ComputeDevicePool
+    from cocos_b200.numerics import random as rnd
+    from oracle import c_oracle
+    pool = ComputeDevicePool()
+    n = 40_000_001
+    for anti in (True, False):
+        rnd.seed(21)
+        got = mcp.count_inside(n, anti, compute_device_pool=pool)
+        assert got == c_oracle.pi_inside(n, 21, 0, anti)         # bit-exact whatever the number of GPUs
+    rnd.seed(21)
+    assert abs(mcp.estimate_pi(400_000_000, batches=4, antithetic=True, compute_device_pool=pool) - math.pi) < 5e-4
+    pool.close()
+
+
+@needs2
 def test_torchrun_bench_two_ranks(golden_values):
     """bench.py under torchrun: one rank per GPU, NCCL allreduce inside the C library."""
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")

@@ -43,6 +43,12 @@ def test_estimate_pi_config2(gpu_device):
     assert abs(est20 - math.pi) < 5 * 1.64 / math.sqrt(1e9) + 1e-4
     with pytest.raises(NotImplementedError):
         mcp.estimate_pi(10, gpu=False)
+    from cocos_b200.multi_processing import ComputeDevicePool
+    from oracle import c_oracle
+    pool = ComputeDevicePool(compute_devices=[0])                    # pool path on one device
+    rnd.seed(3)
+    assert mcp.count_inside(1_000_001, True, compute_device_pool=pool) == c_oracle.pi_inside(1_000_001, 3, 0, True)
+    pool.close()
 
 
 def test_payoff_from_array_matches_reference_price(gpu_device, golden_heston, ref_params):
