@@ -103,8 +103,10 @@ heston_conditional_kernel(const __grid_constant__ FusedConsts<float> c, ReduceWo
         };
 
         uint4 cur = rng.block(0u, keys);
+        uint64_t m1b = 0;
         for (uint32_t b = 0; b < calls; ++b) {
-            const uint4 nxt = rng.block(b + 1, keys);                 // software-pipelined next block
+            m1b += kPhiloxM1;
+            const uint4 nxt = rng.block_from_product(m1b, keys);      // software-pipelined next block
             float wa, wb;
             cond_draw(cur.x, cond_angle(cur.w, cur.x, one_bits), k, wa, wb);
             cond_step(s, wa, k);

@@ -227,13 +227,15 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             uint4 cur[PPT];
 #pragma unroll
             for (int q = 0; q < PPT; ++q) cur[q] = rng[q].template block<ROUNDS>(0u, keys);
+            uint64_t m1b = 0;                                   // M1 * (index of the block being prefetched)
 #pragma unroll((MINB == 1 && !TRAJ) ? 2 : 1)
             for (uint32_t b = 0; b < calls; ++b) {
                 uint4 nxt[PPT];
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
+                m1b += kPhiloxM1;
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) {
-                    nxt[q] = rng[q].template block<ROUNDS>(b + 1, keys);
+                    nxt[q] = rng[q].template block_from_product<ROUNDS>(m1b, keys);
                     split_draws(cur[q], one_bits, d0[q], d1[q], d2[q]);
                 }
                 advance(d0, 3 * b + 1);

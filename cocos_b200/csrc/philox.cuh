@@ -82,8 +82,14 @@ struct PairStream {
 
     template <int ROUNDS = 10>
     __device__ __forceinline__ uint4 block(uint32_t b, const PhiloxKeys& k) const {
-        // round 0 (c0 = plo, c1 = phi, c2 = b, c3 = s): the products are invariant or uniform
-        const uint64_t u1 = (uint64_t)kPhiloxM1 * b;                     // uniform datapath
+        return block_from_product<ROUNDS>((uint64_t)kPhiloxM1 * b, k);
+    }
+
+    // u1 = M1 * block index, which a loop over consecutive blocks advances by one 64-bit addition of M1
+    // (two issue slots) instead of recomputing it with an IMAD.WIDE (four)
+    template <int ROUNDS = 10>
+    __device__ __forceinline__ uint4 block_from_product(uint64_t u1, const PhiloxKeys& k) const {
+        // round 0 (c0 = plo, c1 = phi, c2 = b, c3 = s): the products are invariant or warp-uniform
         uint32_t c0 = ((uint32_t)(u1 >> 32) ^ k.k0[0]) ^ phi;            // 1 LOP3
         uint32_t c1 = (uint32_t)u1;                                      // uniform
         uint32_t c3 = c3_r1;
