@@ -10,3 +10,21 @@ from ._array import ndarray               # noqa: F401
 
 def asnumpy(a):
     return a.to_numpy() if isinstance(a, ndarray) else a
+
+
+def array(obj, dtype=None) -> ndarray:
+    """Host data -> device array (the reference's ``cn.array``, cocos/numerics/_array.py): a plain H2D copy."""
+    import numpy as np
+    from .. import _lib
+    from ..device import current_context
+    from ._array import empty_on
+    if isinstance(obj, ndarray):
+        return obj if dtype is None or np.dtype(dtype) == obj.dtype else obj.astype(dtype)
+    host = np.ascontiguousarray(obj, dtype=dtype)
+    if host.dtype == np.float64 and dtype is None and not isinstance(obj, np.ndarray):
+        host = host.astype(np.float32)                    # Python lists become float32, the device default
+    ctx = current_context()
+    out = empty_on(ctx, host.shape, host.dtype)
+    if host.nbytes:
+        _lib.check(_lib.lib().cb_memcpy_h2d(ctx.handle, out.data_ptr, host.ctypes.data, host.nbytes))
+    return out

@@ -99,6 +99,13 @@ class ndarray:
             shape = tuple(shape[0])
         return ndarray(self._t.reshape(shape), self._ctx)
 
+    def astype(self, dtype):
+        """Type conversion on the device (storage plumbing, done by the allocator's library)."""
+        import torch
+        self._ctx.sync()
+        with torch.cuda.stream(self._ctx.torch_stream()):
+            return ndarray(self._t.to(torch_dtype(dtype)), self._ctx)
+
     def __repr__(self):
         return f"cocos_b200.ndarray(shape={self.shape}, dtype={self.dtype}, device={self._ctx.device})"
 

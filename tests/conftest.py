@@ -15,6 +15,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with `pytest -m gpu`)")
 
 
+def pytest_sessionstart(session):
+    """Build the CUDA library and the C oracle if a fresh checkout has neither (both are git-ignored artefacts)."""
+    import subprocess
+    lib = os.path.join(ROOT, "cocos_b200", "libcocos_b200.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "cocos_b200", "csrc")])
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+
+
 @pytest.fixture(scope="session")
 def golden_values():
     with open(os.path.join(GOLDEN, "reference_values.json")) as fh:

@@ -156,3 +156,15 @@ def test_allreduce_path_on_one_rank(gpu_device, ref_params):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     finally:
         _lib.lib().cb_comm_destroy(comm)
+
+
+def test_array_roundtrip(gpu_device):
+    import cocos_b200.numerics as cn
+    a = np.arange(12, dtype=np.float64).reshape(3, 4)
+    d = cn.array(a)
+    assert d.shape == (3, 4) and d.dtype == np.float64 and np.array_equal(np.array(d), a)
+    assert np.array_equal(cn.asnumpy(d[1]), a[1])
+    f = d.astype(np.float32)
+    assert f.dtype == np.float32 and np.array_equal(f.to_numpy(), a.astype(np.float32))
+    assert cn.array([1.0, 2.0]).dtype == np.float32 and len(cn.array([1.0, 2.0])) == 2
+    assert float(cn.array(np.float32(2.5))) == 2.5
