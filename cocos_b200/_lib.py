@@ -26,6 +26,11 @@ class HestonParams(ctypes.Structure):
     _fields_ = [(n, c_double) for n in ("T", "mu", "kappa", "v_bar", "sigma_v", "rho", "x0", "v0")]
 
 
+class PayoffSpec(ctypes.Structure):
+    """cb_payoff_spec: kind 0 european, 1 asian, 2 up-and-out, 3 down-and-out."""
+    _fields_ = [("kind", c_int), ("is_put", c_int), ("barrier", c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/cocos_b200.h declares
 PROTOTYPES = {
     "cb_last_error": (c_char_p, []),
@@ -72,6 +77,10 @@ PROTOTYPES = {
                                            c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_heston_price_conditional_launch_f32": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64,
                                                        c_u32, c_u64, c_u64, c_void_p, c_void_p, c_void_p]),
+    "cb_heston_payoff_launch_f32": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,
+                                            c_u64, c_u64, c_void_p, P(PayoffSpec)]),
+    "cb_heston_payoff_launch_f64": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,
+                                            c_u64, c_u64, c_void_p, P(PayoffSpec)]),
     "cb_heston_price_finish": (c_int, [c_void_p, c_int, P(c_double), P(c_double)]),
     "cb_call_payoff_sums_f32": (c_int, [c_void_p, c_void_p, c_u64, P(c_double), c_int, P(c_double), P(c_double)]),
     "cb_call_payoff_sums_f64": (c_int, [c_void_p, c_void_p, c_u64, P(c_double), c_int, P(c_double), P(c_double)]),

@@ -657,6 +657,10 @@ static FusedConsts<real> make_consts(const cb_heston_params *p, uint64_t R, uint
     k.pair_count = pair_count;
     k.partnered = R / 2;
     k.nK = nK;
+    k.payoff_kind = 0;
+    k.payoff_sign = (real)1;
+    k.barrier_sign = (real)1;
+    k.barrier_log = (real)0;
     k.keys = philox_keys_from_seed(seed);
     for (int i = 0; i < kMaxStrikes; ++i) k.strikes[i] = (real)(i < nK ? strikes[i] : 0.0);
     return k;
@@ -714,7 +718,7 @@ static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, L
 template <typename real>
 static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N, const double *h_strikes,
                                int nK, uint64_t seed, uint32_t subsequence, uint64_t pair_first, uint64_t pair_count,
-                               cb_comm *comm, real *d_x, real *d_v, real *d_traj) {
+                               cb_comm *comm, real *d_x, real *d_v, real *d_traj, const cb_payoff_spec *spec = nullptr) {
     CB_CTX(c);
     int rc = check_heston(p, R, N);
     if (rc) return rc;
@@ -728,11 +732,25 @@ static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R,
         rc = need_nccl();
         if (rc) return rc;
     }
-    const FusedConsts<real> k = make_consts<real>(p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count);
+    FusedConsts<real> k = make_consts<real>(p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count);
+    if (spec != nullptr) {
+        CB_REQUIRE(spec->kind >= 0 && spec->kind <= 3, "payoff kind must be 0 (european), 1 (asian), 2 (up-and-out), 3 (down-and-out)");
+        CB_REQUIRE(d_traj == nullptr, "path-dependent payoffs and trajectory output are separate launches");
+        k.payoff_kind = spec->kind >= 2 ? 2 : spec->kind;
+        k.payoff_sign = (real)(spec->is_put ? -1.0 : 1.0);
+        if (spec->kind >= 2) {
+            CB_REQUIRE(spec->barrier > 0.0, "the barrier level must be positive");
+            const double sgn = spec->kind == 2 ? 1.0 : -1.0;
+            k.barrier_sign = (real)sgn;
+            k.barrier_log = (real)(sgn * std::log(spec->barrier));
+        }
+    }
     if (pair_count > 0) {
         LaunchShape shape;
         rc = choose_shape<real>(c, pair_count, nK > 1, d_traj != nullptr, &shape);
         if (rc) return rc;
+        if (k.payoff_kind != 0 || k.payoff_sign < (real)0) shape.variant = 0;
+        if (k.payoff_kind != 0) shape.pairs_per_thread = 1;
         CB_CUDA(launch_heston_fused<real>(k, shape, c->ws, d_x, d_v, d_traj, c->stream));
     } else {
         CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));   // an empty shard adds nothing
@@ -749,6 +767,24 @@ extern "C" CB_API int cb_heston_price_launch_f32(cb_ctx *c, const cb_heston_para
                                           float *d_v, float *d_traj) {
     return heston_price_launch<float>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm, d_x,
                                       d_v, d_traj);
+}
+
+extern "C" CB_API int cb_heston_payoff_launch_f32(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                  const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                                  uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                                                  const cb_payoff_spec *spec) {
+    CB_REQUIRE(spec != nullptr, "spec is NULL");
+    return heston_price_launch<float>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm,
+                                      nullptr, nullptr, nullptr, spec);
+}
+
+extern "C" CB_API int cb_heston_payoff_launch_f64(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                  const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                                  uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                                                  const cb_payoff_spec *spec) {
+    CB_REQUIRE(spec != nullptr, "spec is NULL");
+    return heston_price_launch<double>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm,
+                                       nullptr, nullptr, nullptr, spec);
 }
 
 extern "C" CB_API int cb_heston_price_launch_f64(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,

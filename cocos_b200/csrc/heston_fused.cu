@@ -136,7 +136,8 @@ struct PairStore<4> {
 
 // ---- the kernel -------------------------------------------------------------
 
-template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1, int ROUNDS = 10>
+// PAYOFF: 0 terminal (European), 1 arithmetic-average Asian, 2 knock-out barrier -- path functionals in registers
+template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1, int ROUNDS = 10, int PAYOFF = 0>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace ws,
                     real *__restrict__ x_out, real *__restrict__ v_out, real *__restrict__ traj) {
@@ -191,10 +192,28 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
         }
 
         // one Euler step for every pair of this thread from one (radius, angle) word pair each
+        // path functionals of the path-dependent payoffs: sum of S_t (Asian) or running extreme of x_t (barrier)
+        real f1[PPT], f2[PPT];
+        real run_shift = c.x0;                       // x0 + t*mu*dt: the drift the loop keeps out of x1/x2
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) f1[q] = f2[q] = (PAYOFF == 2) ? (real)-3.0e38 : (real)0;
         auto advance = [&](const StepDraw (&d)[PPT], uint32_t step_no) {
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
                 euler_pair(x1[q], v1[q], x2[q], v2[q], d[q].t_radius, d[q].t_angle, k);
+            }
+            if constexpr (PAYOFF != 0) {
+                run_shift += c.mu_dt;
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) {
+                    if constexpr (PAYOFF == 1) {
+                        f1[q] += exp_real(x1[q] + run_shift);
+                        f2[q] += exp_real(x2[q] + run_shift);
+                    } else {
+                        f1[q] = fmax(f1[q], c.barrier_sign * (x1[q] + run_shift));
+                        f2[q] = fmax(f2[q], c.barrier_sign * (x2[q] + run_shift));
+                    }
+                }
             }
             if constexpr (TRAJ) {
                 // row pointers advance by one row per step; the store mode was fixed once per pair block:
@@ -274,7 +293,17 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
                 if (active[q]) { x_out[local[q]] = xT1; v_out[local[q]] = vT1; }
                 if (paired[q]) { x_out[c.pair_count + local[q]] = xT2; v_out[c.pair_count + local[q]] = vT2; }
             }
-            acc.add(exp_real(xT1), exp_real(xT2), active[q], paired[q], c.strikes[0], s_strikes, lane);
+            real S1 = exp_real(xT1), S2 = exp_real(xT2);
+            if constexpr (PAYOFF == 1) {                      // average of the N-1 monitored prices
+                const real inv_n = (real)1 / (real)c.steps;
+                S1 = f1[q] * inv_n;
+                S2 = f2[q] * inv_n;
+            } else if constexpr (PAYOFF == 2) {               // knocked out: a price that makes the payoff vanish
+                const real dead = c.payoff_sign > (real)0 ? (real)0 : (real)3.0e38;
+                if (f1[q] >= c.barrier_log) S1 = dead;
+                if (f2[q] >= c.barrier_log) S2 = dead;
+            }
+            acc.add(S1, S2, active[q], paired[q], c.strikes[0], s_strikes, lane, c.payoff_sign);
         }
     }
     acc.publish(c.nK, ws);
@@ -307,6 +336,16 @@ template <typename real>
 cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s, ReduceWorkspace ws,
                                 real *d_x, real *d_v, real *d_traj, cudaStream_t stream) {
     const bool multi = c.nK > 1;
+    if (c.payoff_kind != 0) {
+        if (d_traj != nullptr) return cudaErrorInvalidValue;
+        void *args[] = {(void *)&c, (void *)&ws, (void *)&d_x, (void *)&d_v, (void *)&d_traj};
+        const void *fn = c.payoff_kind == 1
+            ? (multi ? (const void *)heston_fused_kernel<real, 1, true, false, true, 1, 10, 1>
+                     : (const void *)heston_fused_kernel<real, 1, false, false, true, 1, 10, 1>)
+            : (multi ? (const void *)heston_fused_kernel<real, 1, true, false, true, 1, 10, 2>
+                     : (const void *)heston_fused_kernel<real, 1, false, false, true, 1, 10, 2>);
+        return cudaLaunchKernel(fn, dim3(s.blocks), dim3(s.threads), args, 0, stream);
+    }
     if (d_traj != nullptr) return launch_one<real, 4, true, true, true, 2>(c, s, ws, d_x, d_v, d_traj, stream);
     if constexpr (sizeof(real) == 4) {
         if (!multi && s.variant > 0) {

@@ -38,6 +38,11 @@ struct FusedConsts {
     uint64_t pair_count;
     uint64_t partnered;  // floor(R/2): pairs with global index < partnered own two paths
     int nK;
+    // payoff (0 = terminal/European, 1 = arithmetic-average Asian, 2 = knock-out barrier, discretely monitored)
+    int payoff_kind;
+    real payoff_sign;    // +1 call, -1 put
+    real barrier_sign;   // +1 up-and-out, -1 down-and-out
+    real barrier_log;    // barrier_sign * log(barrier level)
     PhiloxKeys keys;
     real strikes[kMaxStrikes];
 };

@@ -23,11 +23,12 @@ struct PayoffAccumulator {
 
     // S1, S2: terminal prices of a pair; active: the pair exists; paired: its partner exists.
     // Every lane of the warp must call this together (MULTI shuffles).
+    // sign = +1 prices calls max(S-K,0), sign = -1 puts max(K-S,0).
     __device__ __forceinline__ void add(real S1, real S2, bool active, bool paired, real K0, const real *s_strikes,
-                                        unsigned lane) {
+                                        unsigned lane, real sign = (real)1) {
         if constexpr (!MULTI) {
-            const real p1 = active ? fmax(S1 - K0, (real)0) : (real)0;
-            const real p2 = paired ? fmax(S2 - K0, (real)0) : (real)0;
+            const real p1 = active ? fmax(sign * (S1 - K0), (real)0) : (real)0;
+            const real p2 = paired ? fmax(sign * (S2 - K0), (real)0) : (real)0;
             const double tot = (double)(p1 + p2);
             const double unit = paired ? 0.5 * tot : tot;
             sum[0] += tot;
@@ -43,8 +44,8 @@ struct PayoffAccumulator {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const real K = s_strikes[lane + 32 * h];
-                    const real p1 = g1 * fmax(s1 - K, (real)0);
-                    const real p2 = g2 * fmax(s2 - K, (real)0);
+                    const real p1 = g1 * fmax(sign * (s1 - K), (real)0);
+                    const real p2 = g2 * fmax(sign * (s2 - K), (real)0);
                     const double tot = (double)(p1 + p2);
                     const double unit = tot * (0.5 + 0.5 * (double)(g1 - g2));   // 0.5*tot if paired, tot if single
                     sum[h] += tot;

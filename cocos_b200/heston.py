@@ -202,3 +202,46 @@ def simulate_and_compute_option_price_gpu(
     sums, _ = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, total, [K],
                                  compute_device_pool=compute_device_pool)
     return float(math.exp(-r * T) * sums[0] / total)
+
+
+PAYOFF_KINDS = {"european": 0, "asian": 1, "up_and_out": 2, "down_and_out": 3}
+
+
+def price_path_dependent(x0, v0, r, rho, sigma_v, kappa, v_bar, T, K, nT, R, kind: str = "asian", option: str = "call",
+                         barrier: tp.Optional[float] = None, dtype=np.float32,
+                         compute_device_pool: tp.Optional[ComputeDevicePool] = None):
+    """Price and standard error of a path-dependent option on the simulated Heston paths (one fused launch).
+
+    kind: "european", "asian" (arithmetic average of the nT-1 simulated prices), "up_and_out" / "down_and_out"
+    (knock-out monitored at the simulated dates, ``barrier`` is a price level); option: "call" or "put";
+    ``K`` may be a sequence of up to 64 strikes sharing the paths (arrays are returned then).
+    The reference only motivates these payoffs (README.md:376-382); the path functionals live in registers.
+    """
+    if kind not in PAYOFF_KINDS:
+        raise ValueError(f"kind must be one of {tuple(PAYOFF_KINDS)}")
+    if option not in ("call", "put"):
+        raise ValueError("option must be 'call' or 'put'")
+    if PAYOFF_KINDS[kind] >= 2 and (barrier is None or barrier <= 0):
+        raise ValueError("a positive barrier level is required for knock-out payoffs")
+    strikes = list(K) if isinstance(K, (list, tuple, np.ndarray)) else [K]
+    R, nT = int(R), int(nT)
+    p = _params(T, r, kappa, v_bar, sigma_v, rho, x0, v0)
+    spec = _lib.PayoffSpec(PAYOFF_KINDS[kind], int(option == "put"), float(barrier or 0.0))
+    seed, sub = _random.get_seed(), _random.next_subsequence()
+    L = _lib.lib()
+    launch = getattr(L, f"cb_heston_payoff_launch_{_suffix(dtype)}")
+    k_arr, nK = _lib.strikes_array(strikes)
+    pairs = (R + 1) // 2
+    if compute_device_pool is None:
+        ctx = current_context()
+        _lib.check(launch(ctx.handle, ctypes.byref(p), R, nT, k_arr, nK, seed, sub, 0, pairs, None, ctypes.byref(spec)))
+        sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+        _lib.check(L.cb_heston_price_finish(ctx.handle, nK, sums, sumsq))
+    else:
+        def shard_launch(ctx_h, params, R_, N_, k, nk, sd, sb, first, count, comm, dx, dv, dtraj):
+            return launch(ctx_h, params, R_, N_, k, nk, sd, sb, first, count, comm, ctypes.byref(spec))
+        sums, sumsq = compute_device_pool.heston_sums(p, R, nT, strikes, seed, sub, _suffix(dtype), launcher=shard_launch)
+    price, se = _price_from_sums(r, T, R, list(sums), list(sumsq))
+    if isinstance(K, (list, tuple, np.ndarray)):
+        return price, se
+    return float(price[0]), float(se[0])

@@ -156,10 +156,14 @@ class ComputeDevicePool:
         return self._comms
 
     def heston_sums(self, params: "_lib.HestonParams", R: int, N: int, strikes, seed: int, subsequence: int,
-                    dtype_suffix: str = "f32", scheme: str = "euler") -> tp.Tuple[tp.List[float], tp.List[float]]:
-        """Shard ceil(R/2) antithetic pairs over the pool; one NCCL allreduce; returns (sums, sumsq)."""
+                    dtype_suffix: str = "f32", scheme: str = "euler",
+                    launcher=None) -> tp.Tuple[tp.List[float], tp.List[float]]:
+        """Shard ceil(R/2) antithetic pairs over the pool; one NCCL allreduce; returns (sums, sumsq).
+        ``launcher`` (same argument list as cb_heston_price_launch_*) substitutes another fused entry point."""
         L = _lib.lib()
-        if scheme == "conditional":
+        if launcher is not None:
+            launch = launcher
+        elif scheme == "conditional":
             raw = L.cb_heston_price_conditional_launch_f32
 
             def launch(ctx_h, p, R_, N_, k, nk, sd, sub, first, count, comm, dx, dv, dtraj):

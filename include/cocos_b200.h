@@ -51,6 +51,15 @@ typedef struct {
     double T, mu, kappa, v_bar, sigma_v, rho, x0, v0;
 } cb_heston_params;
 
+/* Path-dependent payoffs evaluated inside the fused kernel (the reference only motivates
+ * them, README.md:376-382).  kind 0: European (terminal price), 1: arithmetic-average Asian over the N-1 simulated
+ * dates, 2: up-and-out, 3: down-and-out (knock-out monitored at the N-1 simulated dates, `barrier` = price level). */
+typedef struct {
+    int kind;
+    int is_put;        /* 0: max(S-K,0), 1: max(K-S,0) */
+    double barrier;
+} cb_payoff_spec;
+
 #define CB_MAX_STRIKES 64
 #define CB_UNIQUE_ID_BYTES 128
 
@@ -173,6 +182,15 @@ CB_API int cb_heston_price_launch_f64(cb_ctx *ctx, const cb_heston_params *p, ui
                                uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
                                double *d_x, double *d_v, double *d_traj);
 CB_API int cb_heston_price_finish(cb_ctx *ctx, int nK, double *h_sum, double *h_sumsq);
+/* Same fused simulation with a path-dependent (or put) payoff; sums are collected with cb_heston_price_finish. */
+CB_API int cb_heston_payoff_launch_f32(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                       const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                       uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                                       const cb_payoff_spec *spec);
+CB_API int cb_heston_payoff_launch_f64(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                       const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                       uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                                       const cb_payoff_spec *spec);
 /* Opt-in scheme with the same law of terminal prices (and of antithetic pairs) as the Euler kernel above but half
  * the normals: the log price is sampled conditionally on the variance path (csrc/heston_conditional.cu).  Statistical
  * mode only (no trajectory); results are collected with cb_heston_price_finish. */

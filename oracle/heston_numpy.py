@@ -82,7 +82,7 @@ def uniform_antithetic(shape, axis, dtype=np.float32, draw=None):
 # --------------------------------------------------------------------------
 
 def heston_terminal(T, N, R, mu, kappa, v_bar, sigma_v, rho, x0, v0,
-                    dtype=np.float32, half_normals=None):
+                    dtype=np.float32, half_normals=None, record=None):
     """N-1 Euler steps of (log price x, variance v) for R antithetic paths.
 
     ``half_normals(step)`` -> float64 array (ceil(R/2), 2) of standard normals for
@@ -107,6 +107,8 @@ def heston_terminal(T, N, R, mu, kappa, v_bar, sigma_v, rho, x0, v0,
         v_next = v + kappa * (v_bar - v) * dt + sigma_v * np.multiply(root_v, np.dot(dB, mix))
         v = np.maximum(v_next, F32_EPS)
         x = x_next
+        if record is not None:
+            record.append(x.copy())         # log prices at the simulated dates 1..N-1 (path-dependent payoffs)
     return x, np.maximum(v, F32_EPS)
 
 
@@ -297,3 +299,33 @@ def conditional_model(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, R, seed, sub
     xa = base - 0.5 * dt * A + (rho / sigma_v) * P1 + orth * G1
     xb = base - 0.5 * dt * B - (rho / sigma_v) * P2 + orth * G2
     return np.concatenate([xa, xb[:F]]), np.concatenate([v1, v2[:F]])
+
+
+def path_dependent_sums(x_path, strikes, kind="asian", put=False, barrier=None):
+    """(sum of payoffs, sum of squared pair-unit averages) for path-dependent payoffs on recorded log-price paths.
+
+    x_path: (N-1, R) log prices at the simulated dates (heston_terminal(record=[...])).  Textbook definitions:
+    asian = arithmetic average of the N-1 prices; up/down-and-out = knocked out when any monitored price is
+    >= / <= the barrier, otherwise the European payoff.
+    """
+    X = np.asarray(x_path, dtype=np.float64)
+    S = np.exp(X)
+    R = X.shape[1]
+    H = (R + 1) // 2
+    terminal = S[-1]
+    if kind == "asian":
+        level, alive = S.mean(axis=0), np.ones(R, dtype=bool)
+    elif kind == "up_and_out":
+        level, alive = terminal, X.max(axis=0) < math.log(barrier)
+    elif kind == "down_and_out":
+        level, alive = terminal, X.min(axis=0) > math.log(barrier)
+    else:
+        level, alive = terminal, np.ones(R, dtype=bool)
+    sums, sumsq = [], []
+    for K in np.atleast_1d(np.asarray(strikes, dtype=np.float64)):
+        pay = np.maximum((K - level) if put else (level - K), 0.0) * alive
+        unit = pay[:H].copy()
+        unit[:R // 2] = 0.5 * (pay[:R // 2] + pay[H:])
+        sums.append(pay.sum())
+        sumsq.append((unit * unit).sum())
+    return np.array(sums), np.array(sumsq)
