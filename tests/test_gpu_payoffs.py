@@ -61,7 +61,8 @@ def test_sums_match_oracle(ctx, P, dtype, kind, name, barrier, put):
     np.testing.assert_allclose(s, want_s, rtol=2e-4, atol=slack + 1e-3)
     np.testing.assert_allclose(q, want_q, rtol=5e-4, atol=slack + 1e-3)
     one_s, one_q = payoff_launch(ctx, P, R, N, strikes[1:2], 13, 4, kind, put, barrier or 0.0, dtype)
-    assert one_s[0] == pytest.approx(s[1], rel=1e-9) and one_q[0] == pytest.approx(q[1], rel=1e-9)
+    # single- and multi-strike kernels are separate instantiations: equal up to float32 rounding of the path functionals
+    assert one_s[0] == pytest.approx(s[1], rel=1e-6) and one_q[0] == pytest.approx(q[1], rel=1e-6)
 
 
 def test_limits_and_orderings(ctx, P, gpu_device, ref_params):
