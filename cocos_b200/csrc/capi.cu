@@ -98,22 +98,14 @@ extern "C" CB_API int cb_device_attributes(int dev, int *sm_count, int *cc_major
     return CB_OK;
 }
 
-extern "C" CB_API int cb_ctx_create(int dev, void *stream_or_null, cb_ctx **out) {
-    CB_REQUIRE(out != nullptr, "out is NULL");
-    int n = 0;
-    int rc = cb_device_count(&n);
-    if (rc != CB_OK) return rc;
-    CB_REQUIRE(dev >= 0 && dev < n, "device %d out of range (%d devices)", dev, n);
-    CB_CUDA(cudaSetDevice(dev));
-    cb_ctx *c = new cb_ctx();
-    c->dev = dev;
+static int ctx_allocate(cb_ctx *c, void *stream_or_null) {
     if (stream_or_null != nullptr) {
         c->stream = (cudaStream_t)stream_or_null;
     } else {
         CB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    CB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->dev));
     CB_CUDA(cudaMalloc(&c->ws.partials, sizeof(double) * (size_t)kMaxGridBlocks * kMaxAcc));
     CB_CUDA(cudaMalloc(&c->ws.ticket, sizeof(unsigned int)));
     CB_CUDA(cudaMalloc(&c->ws.result, sizeof(double) * kMaxAcc));
@@ -123,6 +115,28 @@ extern "C" CB_API int cb_ctx_create(int dev, void *stream_or_null, cb_ctx **out)
     CB_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * (kMaxAcc + 1)));
     CB_CUDA(cudaEventCreate(&c->ev_start));
     CB_CUDA(cudaEventCreate(&c->ev_stop));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_ctx_destroy(cb_ctx *c);
+
+extern "C" CB_API int cb_ctx_create(int dev, void *stream_or_null, cb_ctx **out) {
+    CB_REQUIRE(out != nullptr, "out is NULL");
+    int n = 0;
+    int rc = cb_device_count(&n);
+    if (rc != CB_OK) return rc;
+    CB_REQUIRE(dev >= 0 && dev < n, "device %d out of range (%d devices)", dev, n);
+    CB_CUDA(cudaSetDevice(dev));
+    cb_ctx *c = new cb_ctx();
+    c->dev = dev;
+    rc = ctx_allocate(c, stream_or_null);
+    if (rc != CB_OK) {                       // release whatever was allocated; the error text is already set
+        char keep[sizeof g_err];
+        memcpy(keep, g_err, sizeof keep);
+        cb_ctx_destroy(c);
+        memcpy(g_err, keep, sizeof keep);
+        return rc;
+    }
     *out = c;
     return CB_OK;
 }
@@ -130,16 +144,16 @@ extern "C" CB_API int cb_ctx_create(int dev, void *stream_or_null, cb_ctx **out)
 extern "C" CB_API int cb_ctx_destroy(cb_ctx *c) {
     if (c == nullptr) return CB_OK;
     cudaSetDevice(c->dev);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream != nullptr || !c->own_stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->ws.partials);
     cudaFree(c->ws.ticket);
     cudaFree(c->ws.result);
     cudaFree(c->d_inside);
     cudaFree(c->scratch);
     cudaFreeHost(c->h_result);
-    cudaEventDestroy(c->ev_start);
-    cudaEventDestroy(c->ev_stop);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return CB_OK;
 }
@@ -829,6 +843,7 @@ extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb
                 if (eff > best + 1e-9) { best = eff; blocks = g; }
             }
         }
+        blocks = std::min<uint64_t>(blocks, kMaxGridBlocks);
         const double dt = p->T / (double)(N - 1);
         CB_CUDA(launch_heston_conditional(k, (float)p->sigma_v, (float)p->rho, (float)dt, threads, (int)blocks, c->ws,
                                           d_x, d_v, c->stream));
