@@ -1,0 +1,57 @@
+"""Statistical checks of the fused kernel's draw layout on the CPU model (same bits as the device):
+one Philox block is split into three (radius 23 bit, angle 19 bit) pairs that share word 3 for the low angle bits,
+so independence ACROSS the three steps of a block is worth testing, not just marginal normality."""
+import numpy as np
+from scipy import stats
+
+from oracle import heston_numpy as hn, philox_numpy as px
+
+N = 400_000
+
+
+def block_normals(seed=11, sub=5, block=7):
+    w = px.philox_block(np.arange(N, dtype=np.uint64), block, sub, seed)
+    out = []
+    for j in range(3):
+        z0, z1 = px.box_muller_f64_from_fields(w[j] >> np.uint32(9), px.angle19(w[j], w[3], j))
+        out += [z0, z1]
+    return np.stack(out)            # (6, N): the six normals a pair consumes in three consecutive Euler steps
+
+
+def test_marginals_are_standard_normal():
+    z = block_normals()
+    for row in z:
+        assert stats.kstest(row, "norm").pvalue > 0.001
+        assert abs(row.mean()) < 5 / np.sqrt(N) and abs(row.var() - 1) < 8 / np.sqrt(N)
+
+
+def test_no_dependence_across_the_steps_of_a_block():
+    z = block_normals()
+    bound = 4.5 / np.sqrt(N)
+    corr = np.corrcoef(z)
+    assert np.max(np.abs(corr - np.eye(6))) < bound
+    assert np.max(np.abs(np.corrcoef(z ** 2) - np.eye(6))) < bound           # dependence through the radii
+    ang = np.arctan2(z[1::2], z[0::2])                                       # the three angles
+    rad = z[0::2] ** 2 + z[1::2] ** 2                                        # the three squared radii (chi2_2)
+    assert np.max(np.abs(np.corrcoef(np.vstack([np.cos(ang), np.sin(ang)])) - np.eye(6))) < bound
+    assert np.max(np.abs(np.corrcoef(np.vstack([rad, np.cos(ang)])) - np.eye(6))) < bound
+    for a in ang:
+        assert stats.kstest((a + np.pi) / (2 * np.pi), "uniform").pvalue > 0.001
+    for r2 in rad:
+        assert stats.kstest(r2, "chi2", args=(2,)).pvalue > 0.001
+
+
+def test_angle_fields_partition_word3():
+    """The three 19-bit angle fields use disjoint bits: w_j[8:0] and bits 31-22 / 21-12 / 11-2 of word 3."""
+    w = [np.uint32(0x1FF), np.uint32(0x0AA), np.uint32(0x155)]
+    w3 = np.uint32(0b1111111111_0000000000_1010101010_11)
+    assert int(px.angle19(w[0], w3, 0)) == (0x1FF << 10) | 0b1111111111
+    assert int(px.angle19(w[1], w3, 1)) == (0x0AA << 10) | 0
+    assert int(px.angle19(w[2], w3, 2)) == (0x155 << 10) | 0b1010101010
+
+
+def test_consecutive_blocks_and_pairs_are_uncorrelated():
+    half = hn.philox_half_normals(2 * N, seed=3, subsequence=1)
+    a, b = half(2)[:, 0], half(3)[:, 0]             # last step of block 0, first step of block 1
+    assert abs(np.corrcoef(a, b)[0, 1]) < 4.5 / np.sqrt(N)
+    assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 4.5 / np.sqrt(N)          # neighbouring pairs (counters i, i+1)
