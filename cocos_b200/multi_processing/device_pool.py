@@ -186,8 +186,10 @@ class ComputeDevicePool:
                 _lib.check(L.cb_group_end())
         sums = (ctypes.c_double * nK)()
         sumsq = (ctypes.c_double * nK)()
-        for ctx in reversed(self._contexts):          # every rank holds the reduced sums; read rank 0 last
-            _lib.check(L.cb_heston_price_finish(ctx.handle, nK, sums, sumsq))
+        # every rank holds the reduced sums: read them from the first device, just drain the others
+        _lib.check(L.cb_heston_price_finish(self._contexts[0].handle, nK, sums, sumsq))
+        for ctx in self._contexts[1:]:
+            ctx.sync()
         return list(sums), list(sumsq)
 
     def pi_inside(self, n: int, seed: int, subsequence: int, antithetic: bool) -> int:
