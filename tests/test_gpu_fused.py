@@ -210,3 +210,30 @@ def test_argument_errors(ctx, P):
     from oracle import heston_numpy as hn
     with pytest.raises(TypeError):
         heston.simulate_and_compute_option_price(nT=10, R=10, numerical_package_bundle=object, **hn.REFERENCE_PARAMS)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pair_indices_beyond_32_bits(ctx, P, dtype):
+    """Shards far into a huge simulation: the 64-bit pair index feeds both Philox counter words."""
+    first = 2 ** 32 - 6                       # straddles the 2^32 boundary of the low counter word
+    count, N = 12, 20
+    R = 2 ** 40
+    s, q, x, v = fused(ctx, P, R, N, [0.95], seed=77, sub=9, first=first, count=count, dtype=dtype, outputs=True)
+    xm, vm = model(P, 2 * count, N, 77, 9, dtype, pair_offset=first)
+    np.testing.assert_allclose(x[:2 * count], xm, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(v[:2 * count], vm, rtol=5e-3, atol=5e-6)
+    far = fused(ctx, P, R, N, [0.95], seed=77, sub=9, first=2 ** 38 + 3, count=count, dtype=dtype, outputs=True)
+    xf, _ = model(P, 2 * count, N, 77, 9, dtype, pair_offset=2 ** 38 + 3)
+    np.testing.assert_allclose(far[2][:2 * count], xf, rtol=0, atol=2e-5)
+
+
+def test_tiny_and_degenerate_shapes(ctx, P):
+    """R = 1 (a lone unpaired path), N = 2 (one step), empty shards, with every output mode."""
+    s, q, x, v, traj = fused(ctx, P, 1, 2, [0.95], seed=1, sub=1, outputs=True, traj=True)
+    assert traj.shape == (2, 2) and traj[0, 0] == np.float32(P["x0"]) and traj[1, 0] == x[0]
+    assert s[0] == pytest.approx(max(math.exp(float(x[0])) - 0.95, 0.0), rel=1e-5) and q[0] == pytest.approx(s[0] ** 2, rel=1e-5)
+    empty = fused(ctx, P, 10, 5, [0.9, 1.0], seed=1, sub=1, first=5, count=0)
+    assert np.all(empty[0] == 0) and np.all(empty[1] == 0)
+    odd = fused(ctx, P, 3, 4, [0.95], seed=1, sub=1, outputs=True)
+    xm, _ = model(P, 3, 4, 1, 1, np.float32)
+    np.testing.assert_allclose(odd[2][:3], xm, atol=1e-5)
