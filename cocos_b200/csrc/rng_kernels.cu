@@ -5,8 +5,10 @@
 //   rand_antithetic                cocos/numerics/random.py:219-245
 //
 // Element order (CPU model: oracle/philox_numpy.py rand_f32 / randn_f32_model / ...):
-//   f32: elements 4j..4j+3 come from the four words of Philox(index=j, block=0, subsequence)
-//        uniform: u01(o0..o3); normal: Box-Muller(o0,o1) -> (4j, 4j+1), Box-Muller(o2,o3) -> (4j+2, 4j+3)
+//   f32 uniform: elements 4j..4j+3 = u01(o0..o3) of Philox(index=j, block=0, subsequence)
+//   f32 normal (randn): elements 6j..6j+5 = the three Box-Muller pairs of block j, split like the fused Heston
+//        kernel (radius w_d >> 9, angle w_d[8:0]:w3 bits); the antithetic kernels keep two pairs per block:
+//        Box-Muller(o0,o1) -> (4j, 4j+1), Box-Muller(o2,o3) -> (4j+2, 4j+3)
 //   f64: elements 2j, 2j+1 from Philox(index=j): uniform u52(o0,o1), u52(o2,o3);
 //        normal: one Box-Muller pair from U = 1-u52(o0,o1), t = u52(o2,o3)
 // Each thread produces 16 bytes per Philox call and stores them as one vector.
@@ -140,6 +142,50 @@ random_antithetic_kernel(real *__restrict__ out, uint64_t outer, uint64_t d, uin
     }
 }
 
+// float32 normals, six per Philox block: the three (23-bit radius, 19-bit angle) draws of the fused Heston kernel
+// (the Philox call, ~100 issue cycles, is what bounds these fills, so the block is used to the last bit).
+// A warp produces 192 consecutive floats; they are transposed through shared memory so that the global stores
+// are 16-byte vectors covering 768 contiguous bytes.
+__global__ void __launch_bounds__(256)
+randn6_fill_kernel(float *__restrict__ out, uint64_t n, const __grid_constant__ PhiloxKeys k, uint32_t subseq) {
+    __shared__ __align__(16) float s_tile[8][192];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_blocks = (n + 5) / 6;
+    const uint64_t n_tiles = (n_blocks + 31) / 32;
+    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += warps_total) {
+        const uint64_t j = tile * 32 + lane;
+        const uint4 o = philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, subseq, k);
+        float v[6];
+        const uint32_t w[3] = {o.x, o.y, o.z};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const uint32_t field = (__funnelshift_l(o.w << (10 * d), w[d], 14) & 0x007FFFF0u) | 0x3F800000u;
+            const float r = mufu_sqrt(mufu_lg2(2.0f - mantissa_float(w[d])) * -1.3862943611198906f);
+            const float theta = fmaf(__uint_as_float(field), kTwoPi, -kThreePi);
+            v[2 * d] = r * mufu_cos(theta);
+            v[2 * d + 1] = r * mufu_sin(theta);
+        }
+        float2 *mine = reinterpret_cast<float2 *>(&s_tile[warp][lane * 6]);
+        mine[0] = make_float2(v[0], v[1]);
+        mine[1] = make_float2(v[2], v[3]);
+        mine[2] = make_float2(v[4], v[5]);
+        __syncwarp();
+        const uint64_t base = tile * 192;
+        if (aligned && base + 192 <= n) {
+            const float4 *src = reinterpret_cast<const float4 *>(s_tile[warp]);
+            float4 *dst = reinterpret_cast<float4 *>(out + base);
+            __stcs(dst + lane, src[lane]);
+            if (lane < 16) __stcs(dst + 32 + lane, src[32 + lane]);
+        } else {
+            for (uint32_t e = lane; e < 192; e += 32)
+                if (base + e < n) out[base + e] = s_tile[warp][e];
+        }
+        __syncwarp();
+    }
+}
+
 static int fill_grid(uint64_t n_blocks) {
     uint64_t b = (n_blocks + 255) / 256;
     if (b < 1) b = 1;
@@ -158,6 +204,13 @@ cudaError_t launch_philox_words(uint32_t *d_out, uint64_t n_blocks, uint64_t fir
 template <typename real, bool NORMAL>
 cudaError_t launch_random_fill(real *d_out, uint64_t n, const PhiloxKeys &k, uint32_t subseq, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
+    if constexpr (NORMAL && sizeof(real) == 4) {
+        const uint64_t tiles = ((n + 5) / 6 + 31) / 32;
+        const uint64_t cap = 148ull * 8;
+        const uint64_t blocks = (tiles + 7) / 8;
+        randn6_fill_kernel<<<(int)(blocks < cap ? (blocks ? blocks : 1) : cap), 256, 0, s>>>(d_out, n, k, subseq);
+        return cudaGetLastError();
+    }
     constexpr int W = Draw<real, NORMAL>::W;
     random_fill_kernel<real, NORMAL><<<fill_grid((n + W - 1) / W), 256, 0, s>>>(d_out, n, k, subseq);
     return cudaGetLastError();

@@ -143,7 +143,20 @@ def rand_f32(n, seed, subsequence):
 
 
 def randn_f32_model(n, seed, subsequence):
-    """float64 model of cb_randn_f32: elements 4j..4j+3 = (z0,z1)(o0,o1),(z0,z1)(o2,o3)."""
+    """float64 model of cb_randn_f32: elements 6j..6j+5 = the three (radius 23 bit, angle 19 bit) Box-Muller pairs
+    of Philox block j (the split of the fused Heston kernel)."""
+    n = int(n)
+    nblk = (n + 5) // 6
+    o = philox_block(np.arange(nblk, dtype=np.uint64), 0, subsequence, seed)
+    cols = []
+    for d in range(3):
+        cols += list(box_muller_f64_from_fields(o[d] >> np.uint32(9), angle19(o[d], o[3], d)))
+    return np.stack(cols, axis=1).reshape(-1)[:n]
+
+
+def randn_pairs_f32_model(n, seed, subsequence):
+    """float64 model of the two-pairs-per-block normals the antithetic kernels draw:
+    elements 4j..4j+3 = (z0,z1)(o0,o1), (z0,z1)(o2,o3)."""
     n = int(n)
     nblk = (n + 3) // 4
     o = philox_block(np.arange(nblk, dtype=np.uint64), 0, subsequence, seed)

@@ -54,7 +54,7 @@ def test_rand_bit_exact(cn, n):
     assert cn.random.get_seed() == 123 and cn.random.get_state() == (123, 2)
 
 
-@pytest.mark.parametrize("n", [2, 7, 4096, 200_001])
+@pytest.mark.parametrize("n", [2, 5, 6, 7, 191, 192, 193, 4096, 200_001])
 def test_randn_close_to_model(cn, n):
     from oracle import philox_numpy as px
     cn.random.seed(5)
@@ -107,7 +107,7 @@ def test_antithetic_layout(cn, shape, axis, dtype):
     un = cn.random.rand_antithetic(shape, axis, dtype, num_pack=cn).to_numpy()
     assert zn.shape == tuple(shape) and zn.dtype == dtype
     if dtype == np.float32:
-        draw_n, draw_u = px.randn_f32_model(n_draw, 77, 0), px.rand_f32(n_draw, 77, 1)
+        draw_n, draw_u = px.randn_pairs_f32_model(n_draw, 77, 0), px.rand_f32(n_draw, 77, 1)
     else:
         draw_n, draw_u = px.randn_f64_model(n_draw, 77, 0), px.rand_f64(n_draw, 77, 1)
     want_n = hn.normal_antithetic(shape, axis, dtype, draw=lambda *s: draw_n.reshape(s))
