@@ -30,14 +30,24 @@ pi_count_kernel(uint64_t n, int antithetic, uint64_t draw_first, uint64_t draw_c
         const float ux[2] = {u01_f32(o.x), u01_f32(o.z)};
         const float uy[2] = {u01_f32(o.y), u01_f32(o.w)};
         unsigned c = 0;
+        const uint64_t j0 = 2 * b;
+        if (j0 >= draw_first && j0 + 1 < draw_end && (j0 + 1 < n_reflected || n_reflected == 0)) {
+            // interior block (almost all of them): both draws are owned and, if antithetic, both are reflected
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const uint64_t j = 2 * b + h;
-            const bool own = j >= draw_first && j < draw_end;
-            const unsigned a = inside(ux[h], uy[h]);
-            const unsigned r = inside(__fsub_rn(1.0f, ux[h]), __fsub_rn(1.0f, uy[h]));
-            c += own ? a : 0u;
-            c += (own && j < n_reflected) ? r : 0u;
+            for (int h = 0; h < 2; ++h) {
+                c += inside(ux[h], uy[h]);
+                if (n_reflected) c += inside(__fsub_rn(1.0f, ux[h]), __fsub_rn(1.0f, uy[h]));
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t j = j0 + h;
+                const bool own = j >= draw_first && j < draw_end;
+                const unsigned a = inside(ux[h], uy[h]);
+                const unsigned r = inside(__fsub_rn(1.0f, ux[h]), __fsub_rn(1.0f, uy[h]));
+                c += own ? a : 0u;
+                c += (own && j < n_reflected) ? r : 0u;
+            }
         }
         count += c;
     }
