@@ -922,7 +922,7 @@ extern "C" CB_API int cb_pi_count_finish(cb_ctx *c, uint64_t *h_inside) {
 extern "C" CB_API int cb_peak_measure(cb_ctx *c, int kind, int repeats, double *ops_per_s, float *ms_best) {
     CB_CTX(c);
     CB_REQUIRE(ops_per_s != nullptr, "ops_per_s is NULL");
-    CB_REQUIRE(kind >= 0 && kind <= 17, "kind must be in [0,17]");
+    CB_REQUIRE(kind >= 0 && kind <= 20, "kind must be in [0,20]");
     if (repeats < 1) repeats = 1;
     size_t bytes = 4096;
     if (kind == 8 || kind == 10) bytes = (size_t)4 << 30;   // far larger than the 126 MB L2

@@ -134,6 +134,54 @@ peak_imad_kernel(uint32_t *out, uint32_t m0, float fa, float fb) {
     if (s == 0x12345678u || t == 123.456f) out[0] = s;
 }
 
+// Blackwell packed FP32: fma.rn.f32x2 (SASS FFMA2).  MODE 0: FFMA2 chains only; MODE 1: each FFMA2 is followed by an
+// independent FFMA; MODE 2: ... by an independent LOP3.  Tells whether an FFMA2 costs one issue slot or two.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+template <int MODE>
+__global__ void __launch_bounds__(256)
+peak_ffma2_kernel(float *out, float fa, float fb, uint32_t m0) {
+    unsigned long long x[kChains];
+    float f[kChains];
+    uint32_t l[kChains];
+    const unsigned long long a2 = pack2(fa, fa), b2 = pack2(fb, fb);
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        x[i] = pack2(1.0f + 0.001f * (threadIdx.x + i), 2.0f + 0.001f * i);
+        f[i] = 1.0f + i;
+        l[i] = threadIdx.x * 2654435761u + i;
+    }
+#pragma unroll 1
+    for (int it = 0; it < kIters; it += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) {
+                x[i] = ffma2(x[i], a2, b2);
+                if constexpr (MODE == 1) f[i] = fmaf(f[i], fa, fb);
+                if constexpr (MODE == 2) l[i] = (l[i] | m0) ^ l[(i + 1) % kChains];
+            }
+    }
+    float s = 0.f;
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[i]));
+        s += lo + hi + f[i];
+        t ^= l[i];
+    }
+    if (s == 123.456f || t == 0x12345678u) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256)
 peak_hbm_write_kernel(float4 *out, size_t n_vec) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -188,6 +236,9 @@ cudaError_t launch_peak_kernel(int kind, int sm_count, void *d_scratch, size_t s
         case 15: peak_imad_kernel<4><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
         case 16: peak_imad_kernel<5><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
         case 17: peak_imad_kernel<6><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        case 18: peak_ffma2_kernel<0><<<grid, threads, 0, s>>>((float *)d_scratch, 1.000001f, 1e-7f, 0x9E3779B9u); *work_done = thread_ops; break;
+        case 19: peak_ffma2_kernel<1><<<grid, threads, 0, s>>>((float *)d_scratch, 1.000001f, 1e-7f, 0x9E3779B9u); *work_done = thread_ops; break;
+        case 20: peak_ffma2_kernel<2><<<grid, threads, 0, s>>>((float *)d_scratch, 1.000001f, 1e-7f, 0x9E3779B9u); *work_done = thread_ops; break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -228,7 +228,8 @@ CB_API int cb_group_end(void);
  * kind: 0 FFMA, 1 MUFU.LG2, 2 MUFU.SQRT, 3 MUFU.SIN, 4 MUFU.EX2, 5 MUFU.RSQ, 6 DFMA,
  *       7 Philox4x32-10 calls, 8 HBM write (bytes), 9 LOP3 (ALU pipe),
  *       10 HBM copy (read+write bytes), 11-17 integer-multiply issue-cost experiments
- *       (IMAD.WIDE alone / with FFMA / with LOP3, IMAD.HI, IMAD lo)
+ *       (IMAD.WIDE alone / with FFMA / with LOP3, IMAD.HI, IMAD lo),
+ *       18-20 packed FFMA2 (fma.rn.f32x2) alone / with FFMA / with LOP3
  * ops_per_s: thread-level operations per second (FFMA counts 1 op = 2 flop). */
 CB_API int cb_peak_measure(cb_ctx *ctx, int kind, int repeats, double *ops_per_s, float *ms_best);
 

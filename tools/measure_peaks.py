@@ -11,7 +11,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cocos_b200 import _lib, device  # noqa: E402
 
 KINDS = {0: "ffma", 1: "mufu_lg2", 2: "mufu_sqrt", 3: "mufu_sin", 4: "mufu_ex2", 5: "mufu_rsq", 6: "dfma",
-         7: "philox_calls", 8: "hbm_write_bytes", 9: "lop3", 10: "hbm_copy_bytes"}
+         7: "philox_calls", 8: "hbm_write_bytes", 9: "lop3", 10: "hbm_copy_bytes",
+         11: "imad_wide", 12: "imad_wide_ffma_pairs", 13: "imad_wide_lop3_pairs", 14: "imad_hi", 15: "imad_lo",
+         18: "ffma2_packed", 19: "ffma2_ffma_pairs", 20: "ffma2_lop3_pairs"}
 
 
 def measure(ctx, kind, repeats=5):
