@@ -82,10 +82,15 @@ PROTOTYPES = {
     "cb_heston_payoff_launch_f64": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,
                                             c_u64, c_u64, c_void_p, P(PayoffSpec)]),
     "cb_heston_price_finish": (c_int, [c_void_p, c_int, P(c_double), P(c_double)]),
+    "cb_heston_price_multi_f32": (c_int, [c_int, P(c_void_p), P(c_void_p), P(HestonParams), c_u64, c_u32, P(c_double),
+                                          c_int, c_u64, c_u32, P(PayoffSpec), P(c_double), P(c_double)]),
+    "cb_heston_price_multi_f64": (c_int, [c_int, P(c_void_p), P(c_void_p), P(HestonParams), c_u64, c_u32, P(c_double),
+                                          c_int, c_u64, c_u32, P(PayoffSpec), P(c_double), P(c_double)]),
     "cb_call_payoff_sums_f32": (c_int, [c_void_p, c_void_p, c_u64, P(c_double), c_int, P(c_double), P(c_double)]),
     "cb_call_payoff_sums_f64": (c_int, [c_void_p, c_void_p, c_u64, P(c_double), c_int, P(c_double), P(c_double)]),
     "cb_pi_count_launch": (c_int, [c_void_p, c_u64, c_u64, c_u32, c_int, c_u64, c_u64, c_void_p]),
     "cb_pi_count_finish": (c_int, [c_void_p, P(c_u64)]),
+    "cb_pi_count_multi": (c_int, [c_int, P(c_void_p), P(c_void_p), c_u64, c_u64, c_u32, c_int, P(c_u64)]),
     "cb_comm_unique_id": (c_int, [c_void_p]),
     "cb_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_void_p, P(c_void_p)]),
     "cb_comm_init_all": (c_int, [c_int, P(c_void_p), P(c_void_p)]),

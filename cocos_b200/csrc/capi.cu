@@ -867,6 +867,55 @@ extern "C" CB_API int cb_heston_price_finish(cb_ctx *c, int nK, double *h_sum, d
     return CB_OK;
 }
 
+// One call for the whole multi-GPU job (SURVEY.md section 8(b) "cb_heston_price_multi"): contiguous pair shards,
+// kernel + allreduce enqueued on every context's stream inside one NCCL group, a single host read at the end.
+template <typename real>
+static int heston_price_multi(int G, cb_ctx *const *ctxs, cb_comm *const *comms, const cb_heston_params *p, uint64_t R,
+                              uint32_t N, const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                              const cb_payoff_spec *spec, double *h_sum, double *h_sumsq) {
+    CB_REQUIRE(G >= 1 && ctxs != nullptr, "need at least one context");
+    CB_REQUIRE(G == 1 || comms != nullptr, "G > 1 needs one communicator per context");
+    for (int g = 0; g < G; ++g) {
+        CB_REQUIRE(ctxs[g] != nullptr, "context %d is NULL", g);
+        CB_REQUIRE(G == 1 || comms[g] != nullptr, "communicator %d is NULL", g);
+    }
+    const bool grouped = G > 1;
+    const uint64_t pairs = (R + 1) / 2, per = (pairs + (uint64_t)G - 1) / (uint64_t)G;
+    int rc = CB_OK;
+    if (grouped) {
+        rc = cb_group_start();
+        if (rc) return rc;
+    }
+    for (int g = 0; g < G && rc == CB_OK; ++g) {
+        const uint64_t first = std::min<uint64_t>((uint64_t)g * per, pairs);
+        const uint64_t count = std::min<uint64_t>(per, pairs - first);
+        rc = heston_price_launch<real>(ctxs[g], p, R, N, h_strikes, nK, seed, subsequence, first, count,
+                                       grouped ? comms[g] : nullptr, nullptr, nullptr, nullptr, spec);
+    }
+    if (grouped) {
+        const int rc_end = cb_group_end();          // always close the group, keep the first error
+        if (rc == CB_OK) rc = rc_end;
+    }
+    if (rc) return rc;
+    rc = cb_heston_price_finish(ctxs[0], nK, h_sum, h_sumsq);   // every rank holds the reduced sums
+    for (int g = 1; g < G && rc == CB_OK; ++g) rc = cb_ctx_sync(ctxs[g]);
+    return rc;
+}
+
+extern "C" CB_API int cb_heston_price_multi_f32(int G, cb_ctx *const *ctxs, cb_comm *const *comms,
+                                                const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                                const cb_payoff_spec *spec, double *h_sum, double *h_sumsq) {
+    return heston_price_multi<float>(G, ctxs, comms, p, R, N, h_strikes, nK, seed, subsequence, spec, h_sum, h_sumsq);
+}
+
+extern "C" CB_API int cb_heston_price_multi_f64(int G, cb_ctx *const *ctxs, cb_comm *const *comms,
+                                                const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                                const cb_payoff_spec *spec, double *h_sum, double *h_sumsq) {
+    return heston_price_multi<double>(G, ctxs, comms, p, R, N, h_strikes, nK, seed, subsequence, spec, h_sum, h_sumsq);
+}
+
 template <typename real>
 static int payoff_sums(cb_ctx *c, const real *d_x, uint64_t R, const double *h_strikes, int nK, double *h_sum,
                        double *h_sumsq) {
@@ -915,6 +964,34 @@ extern "C" CB_API int cb_pi_count_finish(cb_ctx *c, uint64_t *h_inside) {
     CB_CUDA(cudaStreamSynchronize(c->stream));
     *h_inside = *h;
     return CB_OK;
+}
+
+extern "C" CB_API int cb_pi_count_multi(int G, cb_ctx *const *ctxs, cb_comm *const *comms, uint64_t n, uint64_t seed,
+                                        uint32_t subsequence, int antithetic, uint64_t *h_inside) {
+    CB_REQUIRE(G >= 1 && ctxs != nullptr, "need at least one context");
+    CB_REQUIRE(G == 1 || comms != nullptr, "G > 1 needs one communicator per context");
+    for (int g = 0; g < G; ++g) {
+        CB_REQUIRE(ctxs[g] != nullptr, "context %d is NULL", g);
+        CB_REQUIRE(G == 1 || comms[g] != nullptr, "communicator %d is NULL", g);
+    }
+    const bool grouped = G > 1;
+    const uint64_t ndraw = antithetic ? (n + 1) / 2 : n, per = (ndraw + (uint64_t)G - 1) / (uint64_t)G;
+    int rc = CB_OK;
+    if (grouped) {
+        rc = cb_group_start();
+        if (rc) return rc;
+    }
+    for (int g = 0; g < G && rc == CB_OK; ++g) {
+        const uint64_t first = std::min<uint64_t>((uint64_t)g * per, ndraw);
+        rc = cb_pi_count_launch(ctxs[g], n, seed, subsequence, antithetic, first, std::min<uint64_t>(per, ndraw - first),
+                                grouped ? comms[g] : nullptr);
+    }
+    if (grouped) {
+        const int rc_end = cb_group_end();
+        if (rc == CB_OK) rc = rc_end;
+    }
+    for (int g = G - 1; g >= 0 && rc == CB_OK; --g) rc = cb_pi_count_finish(ctxs[g], h_inside);
+    return rc;
 }
 
 // ---------------------------------------------------------------- calibration

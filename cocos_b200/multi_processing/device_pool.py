@@ -161,6 +161,18 @@ class ComputeDevicePool:
         """Shard ceil(R/2) antithetic pairs over the pool; one NCCL allreduce; returns (sums, sumsq).
         ``launcher`` (same argument list as cb_heston_price_launch_*) substitutes another fused entry point."""
         L = _lib.lib()
+        k_arr, nK = _lib.strikes_array(strikes)
+        sums = (ctypes.c_double * nK)()
+        sumsq = (ctypes.c_double * nK)()
+        G = self.number_of_devices
+        comms = self._communicators()
+        if launcher is None and scheme == "euler":
+            # the whole job in one C call: shards, launches, grouped allreduce, one host read
+            ctxs, comm_arr = self._handle_arrays(comms)
+            multi = getattr(L, f"cb_heston_price_multi_{dtype_suffix}")
+            _lib.check(multi(G, ctxs, comm_arr, ctypes.byref(params), R, N, k_arr, nK, seed, subsequence, None, sums,
+                             sumsq))
+            return list(sums), list(sumsq)
         if launcher is not None:
             launch = launcher
         elif scheme == "conditional":
@@ -169,11 +181,8 @@ class ComputeDevicePool:
             def launch(ctx_h, p, R_, N_, k, nk, sd, sub, first, count, comm, dx, dv, dtraj):
                 return raw(ctx_h, p, R_, N_, k, nk, sd, sub, first, count, comm, dx, dv)
         else:
-            launch = getattr(L, f"cb_heston_price_launch_{dtype_suffix}")
-        k_arr, nK = _lib.strikes_array(strikes)
+            raise ValueError(f"unknown scheme {scheme!r}")
         pairs = (R + 1) // 2
-        G = self.number_of_devices
-        comms = self._communicators()
         if comms is not None:
             _lib.check(L.cb_group_start())
         try:
@@ -184,33 +193,24 @@ class ComputeDevicePool:
         finally:
             if comms is not None:
                 _lib.check(L.cb_group_end())
-        sums = (ctypes.c_double * nK)()
-        sumsq = (ctypes.c_double * nK)()
         # every rank holds the reduced sums: read them from the first device, just drain the others
         _lib.check(L.cb_heston_price_finish(self._contexts[0].handle, nK, sums, sumsq))
         for ctx in self._contexts[1:]:
             ctx.sync()
         return list(sums), list(sumsq)
 
+    def _handle_arrays(self, comms):
+        n = self.number_of_devices
+        ctxs = (ctypes.c_void_p * n)(*[c.handle for c in self._contexts])
+        comm_arr = (ctypes.c_void_p * n)(*[c.value for c in comms]) if comms is not None else None
+        return ctxs, comm_arr
+
     def pi_inside(self, n: int, seed: int, subsequence: int, antithetic: bool) -> int:
         """Shard the draws of a Monte-Carlo pi estimate over the pool; one NCCL allreduce of the inside count."""
-        L = _lib.lib()
-        ndraw = (n + 1) // 2 if antithetic else n
-        G = self.number_of_devices
-        comms = self._communicators()
-        if comms is not None:
-            _lib.check(L.cb_group_start())
-        try:
-            for g, ctx in enumerate(self._contexts):
-                first, count = shard_range(ndraw, G, g)
-                _lib.check(L.cb_pi_count_launch(ctx.handle, int(n), seed, subsequence, int(bool(antithetic)), first, count,
-                                                comms[g] if comms is not None else None))
-        finally:
-            if comms is not None:
-                _lib.check(L.cb_group_end())
+        ctxs, comm_arr = self._handle_arrays(self._communicators())
         inside = ctypes.c_uint64(0)
-        for ctx in reversed(self._contexts):
-            _lib.check(L.cb_pi_count_finish(ctx.handle, ctypes.byref(inside)))
+        _lib.check(_lib.lib().cb_pi_count_multi(self.number_of_devices, ctxs, comm_arr, int(n), seed, subsequence,
+                                                int(bool(antithetic)), ctypes.byref(inside)))
         return inside.value
 
     def close(self):

@@ -191,6 +191,16 @@ CB_API int cb_heston_payoff_launch_f64(cb_ctx *ctx, const cb_heston_params *p, u
                                        const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
                                        uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
                                        const cb_payoff_spec *spec);
+/* The whole multi-GPU job of simulate_and_compute_option_price_gpu (heston_utilities.py:217-270) in one call:
+ * shard g of G owns pairs [g*ceil(P/G), min((g+1)*ceil(P/G), P)), P = ceil(R/2); every context's stream gets its
+ * kernel followed by the one ncclAllReduce (grouped); the reduced sums are read once from ctxs[0].  comms may be
+ * NULL when G == 1; spec may be NULL (European call).  Results do not depend on G beyond f64 summation order. */
+CB_API int cb_heston_price_multi_f32(int G, cb_ctx *const *ctxs, cb_comm *const *comms, const cb_heston_params *p,
+                                     uint64_t R, uint32_t N, const double *h_strikes, int nK, uint64_t seed,
+                                     uint32_t subsequence, const cb_payoff_spec *spec, double *h_sum, double *h_sumsq);
+CB_API int cb_heston_price_multi_f64(int G, cb_ctx *const *ctxs, cb_comm *const *comms, const cb_heston_params *p,
+                                     uint64_t R, uint32_t N, const double *h_strikes, int nK, uint64_t seed,
+                                     uint32_t subsequence, const cb_payoff_spec *spec, double *h_sum, double *h_sumsq);
 /* Opt-in scheme with the same law of terminal prices (and of antithetic pairs) as the Euler kernel above but half
  * the normals: the log price is sampled conditionally on the variance path (csrc/heston_conditional.cu).  Statistical
  * mode only (no trajectory); results are collected with cb_heston_price_finish. */
@@ -212,6 +222,9 @@ CB_API int cb_call_payoff_sums_f64(cb_ctx *ctx, const double *d_x, uint64_t R, c
 CB_API int cb_pi_count_launch(cb_ctx *ctx, uint64_t n, uint64_t seed, uint32_t subsequence, int antithetic,
                        uint64_t draw_first, uint64_t draw_count, cb_comm *comm);
 CB_API int cb_pi_count_finish(cb_ctx *ctx, uint64_t *h_inside);
+/* estimate_pi over a device pool in one call (draw shards as above, one allreduce of the count). */
+CB_API int cb_pi_count_multi(int G, cb_ctx *const *ctxs, cb_comm *const *comms, uint64_t n, uint64_t seed,
+                             uint32_t subsequence, int antithetic, uint64_t *h_inside);
 
 /* ---- collectives: stands in for ComputeDevicePool's process pool
  * (cocos/multi_processing/device_pool.py:58-253).  libnccl.so.2 is loaded on

@@ -102,3 +102,74 @@ def test_torchrun_bench_two_ranks(golden_values):
     ref = golden_values["statistical"]["nT501"]
     assert abs(res["price"] - ref["price"]) <= 3 * math.hypot(res["price_se"], ref["se"])
     assert abs(res["e2e"]["price"] - ref["price"]) <= 3 * math.hypot(res["price_se"], ref["se"])
+
+
+def _multi(G, R, N, strikes, seed, sub, suffix="f32", spec=None):
+    """cb_heston_price_multi_* called directly on freshly created contexts/communicators."""
+    import ctypes
+    from cocos_b200 import _lib
+    L = _lib.lib()
+    ctxs = [_lib.Context(d) for d in range(G)]
+    harr = (ctypes.c_void_p * G)(*[c.handle for c in ctxs])
+    comms = None
+    if G > 1:
+        comms = (ctypes.c_void_p * G)()
+        _lib.check(L.cb_comm_init_all(G, harr, comms))
+    k_arr, nK = _lib.strikes_array(strikes)
+    s, q = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+    p = _multi.params
+    rc = getattr(L, f"cb_heston_price_multi_{suffix}")(G, harr, comms, ctypes.byref(p), R, N, k_arr, nK, seed, sub,
+                                                       ctypes.byref(spec) if spec is not None else None, s, q)
+    if comms is not None:
+        for c in comms:
+            L.cb_comm_destroy(ctypes.c_void_p(c))
+    _lib.check(rc)
+    return np.array(s), np.array(q)
+
+
+@pytest.mark.parametrize("suffix", ["f32", "f64"])
+def test_one_call_multi_entry_matches_launch_finish(gpu_device, ref_params, suffix):
+    """The one-call C entry equals launch + finish on one device and is device-count invariant."""
+    import ctypes
+    from cocos_b200 import _lib
+    q = ref_params
+    _multi.params = _lib.HestonParams(q["T"], q["r"], q["kappa"], q["v_bar"], q["sigma_v"], q["rho"], q["x0"], q["v0"])
+    R, N, strikes = 300_001, 64, [0.9, 0.95, 1.0, 1.05]
+    s1, q1 = _multi(1, R, N, strikes, 9, 2, suffix)
+    L = _lib.lib()
+    ctx = _lib.Context(0)
+    k_arr, nK = _lib.strikes_array(strikes)
+    _lib.check(getattr(L, f"cb_heston_price_launch_{suffix}")(ctx.handle, ctypes.byref(_multi.params), R, N, k_arr, nK, 9, 2,
+                                                              0, (R + 1) // 2, None, None, None, None))
+    s0, q0 = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+    _lib.check(L.cb_heston_price_finish(ctx.handle, nK, s0, q0))
+    np.testing.assert_array_equal(s1, np.array(s0))
+    np.testing.assert_array_equal(q1, np.array(q0))
+    spec = _lib.PayoffSpec(1, 0, 0.0)          # Asian call through the same entry
+    sa, _ = _multi(1, R, N, strikes, 9, 2, suffix, spec)
+    assert np.all(sa > 0) and np.all(sa < s1)  # averaging lowers the call value under these parameters
+    if _device_count() >= 2:
+        s2, q2 = _multi(2, R, N, strikes, 9, 2, suffix)
+        np.testing.assert_allclose(s2, s1, rtol=1e-12)
+        np.testing.assert_allclose(q2, q1, rtol=1e-12)
+        sa2, _ = _multi(2, R, N, strikes, 9, 2, suffix, spec)
+        np.testing.assert_allclose(sa2, sa, rtol=1e-12)
+
+
+def test_one_call_multi_entry_argument_errors(gpu_device, ref_params):
+    import ctypes
+    from cocos_b200 import _lib
+    L = _lib.lib()
+    q = ref_params
+    p = _lib.HestonParams(q["T"], q["r"], q["kappa"], q["v_bar"], q["sigma_v"], q["rho"], q["x0"], q["v0"])
+    ctx = _lib.Context(0)
+    harr = (ctypes.c_void_p * 2)(ctx.handle, ctx.handle)
+    k_arr, nK = _lib.strikes_array([1.0])
+    s, sq = (ctypes.c_double * 1)(), (ctypes.c_double * 1)()
+    assert L.cb_heston_price_multi_f32(0, harr, None, ctypes.byref(p), 100, 10, k_arr, nK, 0, 0, None, s, sq) != 0
+    assert L.cb_heston_price_multi_f32(2, harr, None, ctypes.byref(p), 100, 10, k_arr, nK, 0, 0, None, s, sq) != 0
+    assert b"communicator" in L.cb_last_error()
+    inside = ctypes.c_uint64(0)
+    assert L.cb_pi_count_multi(2, harr, None, 1000, 0, 0, 1, ctypes.byref(inside)) != 0
+    _lib.check(L.cb_pi_count_multi(1, harr, None, 1000, 0, 0, 1, ctypes.byref(inside)))
+    assert 700 < inside.value < 870
