@@ -91,6 +91,7 @@ PROTOTYPES = {
     "cb_pi_count_launch": (c_int, [c_void_p, c_u64, c_u64, c_u32, c_int, c_u64, c_u64, c_void_p]),
     "cb_pi_count_finish": (c_int, [c_void_p, P(c_u64)]),
     "cb_pi_count_multi": (c_int, [c_int, P(c_void_p), P(c_void_p), c_u64, c_u64, c_u32, c_int, P(c_u64)]),
+    "cb_nccl_library": (c_int, [ctypes.c_char_p]),
     "cb_comm_unique_id": (c_int, [c_void_p]),
     "cb_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_void_p, P(c_void_p)]),
     "cb_comm_init_all": (c_int, [c_int, P(c_void_p), P(c_void_p)]),
@@ -120,8 +121,26 @@ def lib():
                     fn = getattr(handle, name)      # AttributeError if the header and the library disagree
                     fn.restype = restype
                     fn.argtypes = argtypes
+                bundled = _bundled_nccl()
+                if bundled:
+                    handle.cb_nccl_library(bundled.encode())
                 _lib = handle
     return _lib
+
+
+def _bundled_nccl():
+    """Path of the libnccl.so.2 torch ships (found without importing torch): torch's libtorch_cuda.so needs that
+    version, so it must be the copy this process maps first."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        return None
+    for root in (spec.submodule_search_locations if spec else []):
+        path = os.path.join(root, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            return path
+    return None
 
 
 _ERRORS = {CB_ERR_INVALID: ValueError, CB_ERR_CUDA: RuntimeError, CB_ERR_NCCL: RuntimeError,

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
+#include <cstdlib>
 #include <tuple>
 
 #include "kernels.h"
@@ -268,12 +270,22 @@ struct NcclApi {
 NcclApi g_nccl;
 std::once_flag g_nccl_once;
 
+std::string g_nccl_path;   // cb_nccl_library(); else $COCOS_B200_NCCL_LIBRARY
+
 void load_nccl() {
-    // prefer a libnccl already mapped into the process (torch's bundled copy), else the system one
+    // 1. a libnccl already mapped into the process (the host framework's copy);
+    // 2. the path the host named: a process that later loads a framework built against a NEWER libnccl.so.2 must
+    //    not find an older system copy already resident under the same SONAME;
+    // 3. the system library.
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *nm : names) {
         g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
         if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) {
+        const char *env = getenv("COCOS_B200_NCCL_LIBRARY");
+        const std::string path = !g_nccl_path.empty() ? g_nccl_path : std::string(env ? env : "");
+        if (!path.empty()) g_nccl.handle = dlopen(path.c_str(), RTLD_NOW | RTLD_GLOBAL);
     }
     if (!g_nccl.handle)
         for (const char *nm : names) {
@@ -312,6 +324,13 @@ int need_nccl() {
     } while (0)
 
 static_assert(sizeof(ncclUniqueId) == CB_UNIQUE_ID_BYTES, "unique id size");
+
+extern "C" CB_API int cb_nccl_library(const char *path) {
+    CB_REQUIRE(path != nullptr, "path is NULL");
+    CB_REQUIRE(!g_nccl.ok, "NCCL is already loaded");
+    g_nccl_path = path;
+    return CB_OK;
+}
 
 extern "C" CB_API int cb_comm_unique_id(void *h_id) {
     CB_REQUIRE(h_id != nullptr, "h_id is NULL");

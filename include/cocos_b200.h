@@ -226,6 +226,10 @@ CB_API int cb_pi_count_finish(cb_ctx *ctx, uint64_t *h_inside);
 CB_API int cb_pi_count_multi(int G, cb_ctx *const *ctxs, cb_comm *const *comms, uint64_t n, uint64_t seed,
                              uint32_t subsequence, int antithetic, uint64_t *h_inside);
 
+/* NCCL is loaded lazily on the first communicator call: a copy already mapped into the process wins, then the
+ * path given here (or $COCOS_B200_NCCL_LIBRARY), then the system libnccl.so.2.  Name the host framework's bundled
+ * copy when that framework may be imported AFTER the first communicator is made (same SONAME, newer version). */
+CB_API int cb_nccl_library(const char *path);
 /* ---- collectives: stands in for ComputeDevicePool's process pool
  * (cocos/multi_processing/device_pool.py:58-253).  libnccl.so.2 is loaded on
  * first use. */

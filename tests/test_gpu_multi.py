@@ -173,3 +173,18 @@ def test_one_call_multi_entry_argument_errors(gpu_device, ref_params):
     assert L.cb_pi_count_multi(2, harr, None, 1000, 0, 0, 1, ctypes.byref(inside)) != 0
     _lib.check(L.cb_pi_count_multi(1, harr, None, 1000, 0, 0, 1, ctypes.byref(inside)))
     assert 700 < inside.value < 870
+
+
+def test_nccl_loaded_before_torch_is_the_bundled_copy():
+    """A communicator made before torch is imported must not pin an older system libnccl.so.2 under the SONAME
+    torch's libtorch_cuda.so resolves against (regression: 'undefined symbol: ncclDevCommCreate')."""
+    code = ("import ctypes, sys\n"
+            "from cocos_b200 import _lib\n"
+            "assert 'torch' not in sys.modules\n"
+            "buf = ctypes.create_string_buffer(128)\n"
+            "_lib.check(_lib.lib().cb_comm_unique_id(buf))\n"
+            "import torch\n"
+            "assert torch.cuda.is_available()\n"
+            "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
