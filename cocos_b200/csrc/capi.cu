@@ -706,13 +706,13 @@ template <typename real>
 static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, LaunchShape *s) {
     // defaults from the tools/tune_fused.py sweeps: float 256 threads x 1 pair, double 128 threads x 2 pairs
     const int threads = c->threads ? c->threads : (sizeof(real) == 8 ? 128 : 256);
-    const int ppt = traj ? 4 : (c->ppt ? c->ppt : (sizeof(real) == 8 ? 2 : 1));
+    const int ppt = traj ? 1 : (c->ppt ? c->ppt : (sizeof(real) == 8 ? 2 : 1));
     const int variant = (sizeof(real) == 4 && !multi && !traj) ? c->variant : 0;
-    const auto key = std::make_tuple((int)(sizeof(real) == 8), traj ? -4 : ppt, (int)multi, threads, variant);
+    const auto key = std::make_tuple((int)(sizeof(real) == 8), traj ? -1 : ppt, (int)multi, threads, variant);
     auto it = c->occ_cache.find(key);
     if (it == c->occ_cache.end()) {
         int bps = 0, regs = 0;
-        CB_CUDA((fused_occupancy<real>(threads, traj ? -4 : ppt, multi, variant, &bps, &regs)));
+        CB_CUDA((fused_occupancy<real>(threads, traj ? -1 : ppt, multi, variant, &bps, &regs)));
         it = c->occ_cache.emplace(key, std::make_pair(bps, regs)).first;
     }
     int bps = it->second.first;

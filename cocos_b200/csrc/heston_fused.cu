@@ -27,16 +27,17 @@ constexpr int kMaxThreads = kFusedMaxThreads;
 // ---- per-type math ---------------------------------------------------------
 
 __device__ __forceinline__ float root(float v) { return mufu_sqrt(v); }
-// double sqrt without the IEEE fix-up path: MUFU.RSQ64H seed (~2^-22) + ONE cubically convergent step on 1/sqrt,
-//   e = 1 - p y^2,  y' = y (1 + e/2 + 3 e^2/8)   =>  relative error ~ e^3 ~ 2^-66  (the parity kernel keeps __dsqrt_rn).
-// FP64 instructions cost two issue cycles each on B200, so the step count matters: 7 FP64 + 1 MUFU, no F2F
-// (conversions to/from f64 share the XU pipe).  p = 0 (U = 1) is nudged to 1e-290 so that the seed stays finite.
+// double sqrt without the IEEE fix-up path: MUFU.RSQ64H seed (~2^-22) + ONE Newton step on 1/sqrt folded into the
+// product,  g = p y,  e = 1 - g y,  sqrt p ~ g (1 + e/2)  =>  relative error 3 e^2/8 ~ 2^-45 -- seven orders below the
+// float accuracy of the normals that multiply it (the parity kernel keeps __dsqrt_rn).  FP64 instructions cost two
+// issue cycles each on B200, so the step count matters: 4 FP64 + 1 MUFU, no F2F (conversions share the XU pipe).
+// p > 0 always: euler_pair keeps lg2 U away from zero.
 __device__ __forceinline__ double root(double p) {
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p + 1e-290));
-    const double e = fma(-(p * y), y, 1.0);
-    y = fma(y, e * fma(e, 0.375, 0.5), y);
-    return p * y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+    const double g = p * y;
+    const double e = fma(-g, y, 1.0);
+    return fma(g * 0.5, e, g);
 }
 // min without the NaN bookkeeping of fmin(double) (DSETP + 2 SEL instead of 6 instructions)
 __device__ __forceinline__ float floor_min(float a, float b) { return fminf(a, b); }
@@ -108,7 +109,10 @@ __device__ __forceinline__ void split_draws(const uint4 &o, uint32_t one_bits, S
 template <typename real>
 __device__ __forceinline__ void euler_pair(real &x1, real &u1, real &x2, real &u2, float t_radius, float t_angle,
                                            const StepRegs<real> &k) {
-    const real L = (real)mufu_lg2(2.0f - t_radius);                       // lg2 U <= 0, U in (0,1]
+    float L_f = mufu_lg2(2.0f - t_radius);                                // lg2 U <= 0, U in (0,1]
+    if constexpr (sizeof(real) == 8) L_f -= 1.17549435e-38f;              // U = 1: keeps the rsqrt seed of root() finite;
+                                                                          // every other lg2 U (|.| >= 2^-24) is unchanged
+    const real L = (real)L_f;
     const float theta = fmaf(t_angle, k.two_pi, -kThreePi);               // [-pi,pi)
     const float cs_f = mufu_cos(theta), sn_f = mufu_sin(theta);
     const real cs = (real)cs_f;
@@ -121,19 +125,6 @@ __device__ __forceinline__ void euler_pair(real &x1, real &u1, real &x2, real &u
     u2 = floor_min(fma(q2, -g, fma(u2, k.decay, k.pull_u)), k.floor_u);
 }
 
-template <int N>
-struct PairStore;   // vector store of N consecutive reals
-template <>
-struct PairStore<4> {
-    static __device__ __forceinline__ void put(float *p, const float (&v)[4]) {
-        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-    static __device__ __forceinline__ void put(double *p, const double (&v)[4]) {
-        reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
-        reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
-    }
-};
-
 // ---- the kernel -------------------------------------------------------------
 
 // PAYOFF: 0 terminal (European), 1 arithmetic-average Asian, 2 knock-out barrier -- path functionals in registers
@@ -141,20 +132,17 @@ template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int M
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace ws,
                     real *__restrict__ x_out, real *__restrict__ v_out, real *__restrict__ traj) {
-    static_assert(!TRAJ || PPT == 4, "trajectory mode stores 4 consecutive pairs per thread");
     const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t per_iter = total * PPT;
     const uint64_t iters = (c.pair_count + per_iter - 1) / per_iter;   // same for every thread: warps stay converged
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t row_len = 2 * c.pair_count;
-    const bool vec_ok = TRAJ && (c.pair_count % 4 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(traj) & (4 * sizeof(real) - 1)) == 0);
 
     __shared__ real s_strikes[kMaxStrikes];
     if (MULTI) stage_strikes(s_strikes, c.strikes, c.nK);
     PayoffAccumulator<real, MULTI> acc;
-    const real x_shift = c.x0 + (real)c.steps * c.mu_dt;
+    const real x_shift = fma((real)c.steps, c.mu_dt, c.x0);
     const StepRegs<real> k(c);
     // 0x3F800000 in a register ptxas cannot constant-fold (steps < 2^31 always): keeps angle_float at one LOP3
     const uint32_t one_bits = 0x3F800000u | (c.steps >> 31);
@@ -169,7 +157,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
         real x1[PPT], v1[PPT], x2[PPT], v2[PPT];
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
-            local[q] = TRAJ ? (it * total + gtid) * PPT + q : (it * PPT + q) * total + gtid;
+            local[q] = (it * PPT + q) * total + gtid;      // a warp owns 32 consecutive pairs: coalesced rows
             active[q] = local[q] < c.pair_count;
             const uint64_t gp = c.pair_first + (active[q] ? local[q] : 0);   // idle lanes replay pair 0, masked below
             paired[q] = active[q] && gp < c.partnered;
@@ -177,18 +165,18 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             x1[q] = x2[q] = (real)0;
             v1[q] = v2[q] = k.u0;            // v1/v2 hold u = c1*v inside the time loop
         }
-        real *row1 = nullptr, *row2 = nullptr;      // this thread's slots in the current trajectory row
-        int store_mode = 0;
-        uint32_t edge_mask = 0;                      // bit q: pair q active, bit 4+q: partner of pair q exists
+        // trajectory mode: this thread's slots in the current row [first halves | partners]; a warp writes 128
+        // contiguous bytes per half and step (predicated at the ragged edge), rows advance by row_len per step
+        real *row1[PPT], *row2[PPT];
+        real step_f = (real)0;
         if constexpr (TRAJ) {   // row 0: the initial log price
-            row1 = traj + local[0];
-            row2 = traj + c.pair_count + local[0];
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
-                if (active[q]) { row1[q] = c.x0; edge_mask |= 1u << q; }
-                if (paired[q]) { row2[q] = c.x0; edge_mask |= 16u << q; }
+                row1[q] = traj + local[q];
+                row2[q] = traj + c.pair_count + local[q];
+                if (active[q]) *row1[q] = c.x0;
+                if (paired[q]) *row2[q] = c.x0;
             }
-            store_mode = (vec_ok && edge_mask == 0xFFu) ? 1 : (edge_mask ? 2 : 0);
         }
 
         // one Euler step for every pair of this thread from one (radius, angle) word pair each
@@ -197,7 +185,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
         real run_shift = c.x0;                       // x0 + t*mu*dt: the drift the loop keeps out of x1/x2
 #pragma unroll
         for (int q = 0; q < PPT; ++q) f1[q] = f2[q] = (PAYOFF == 2) ? (real)-3.0e38 : (real)0;
-        auto advance = [&](const StepDraw (&d)[PPT], uint32_t step_no) {
+        auto advance = [&](const StepDraw (&d)[PPT]) {
 #pragma unroll
             for (int q = 0; q < PPT; ++q) {
                 euler_pair(x1[q], v1[q], x2[q], v2[q], d[q].t_radius, d[q].t_angle, k);
@@ -216,23 +204,14 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
                 }
             }
             if constexpr (TRAJ) {
-                // row pointers advance by one row per step; the store mode was fixed once per pair block:
-                // 1 = all four pairs active and partnered, aligned: two 16-byte stores; 2 = ragged edge: scalar
-                const real shift = c.x0 + (real)step_no * c.mu_dt;
-                row1 += row_len;
-                row2 += row_len;
-                if (store_mode == 1) {
-                    real a[PPT], b[PPT];
+                step_f += (real)1;                                   // exact: steps < 2^24
+                const real shift = fma(step_f, c.mu_dt, c.x0);       // the drift the loop keeps out of x1/x2
 #pragma unroll
-                    for (int q = 0; q < PPT; ++q) { a[q] = x1[q] + shift; b[q] = x2[q] + shift; }
-                    PairStore<PPT>::put(row1, a);
-                    PairStore<PPT>::put(row2, b);
-                } else if (store_mode == 2) {
-#pragma unroll
-                    for (int q = 0; q < PPT; ++q) {
-                        if (edge_mask & (1u << q)) row1[q] = x1[q] + shift;
-                        if (edge_mask & (16u << q)) row2[q] = x2[q] + shift;
-                    }
+                for (int q = 0; q < PPT; ++q) {
+                    row1[q] += row_len;
+                    row2[q] += row_len;
+                    if (active[q]) *row1[q] = x1[q] + shift;
+                    if (paired[q]) *row2[q] = x2[q] + shift;
                 }
             }
         };
@@ -247,7 +226,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 #pragma unroll
             for (int q = 0; q < PPT; ++q) cur[q] = rng[q].template block<ROUNDS>(0u, keys);
             uint64_t m1b = 0;                                   // M1 * (index of the block being prefetched)
-#pragma unroll((MINB == 1 && !TRAJ) ? 2 : 1)
+#pragma unroll((MINB == 1 || TRAJ) ? 2 : 1)
             for (uint32_t b = 0; b < calls; ++b) {
                 uint4 nxt[PPT];
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
@@ -257,9 +236,9 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
                     nxt[q] = rng[q].template block_from_product<ROUNDS>(m1b, keys);
                     split_draws(cur[q], one_bits, d0[q], d1[q], d2[q]);
                 }
-                advance(d0, 3 * b + 1);
-                advance(d1, 3 * b + 2);
-                advance(d2, 3 * b + 3);
+                advance(d0);
+                advance(d1);
+                advance(d2);
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) cur[q] = nxt[q];
             }
@@ -267,8 +246,8 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) split_draws(cur[q], one_bits, d0[q], d1[q], d2[q]);
-                advance(d0, 3 * calls + 1);
-                if (rest > 1) advance(d1, 3 * calls + 2);
+                advance(d0);
+                if (rest > 1) advance(d1);
             }
         } else {
             for (uint32_t b = 0; b < calls + (rest ? 1u : 0u); ++b) {
@@ -276,9 +255,9 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 #pragma unroll
                 for (int q = 0; q < PPT; ++q) split_draws(rng[q].template block<ROUNDS>(b, keys), one_bits, d0[q], d1[q], d2[q]);
                 const uint32_t left = c.steps - 3 * b;
-                advance(d0, 3 * b + 1);
-                if (left > 1) advance(d1, 3 * b + 2);
-                if (left > 2) advance(d2, 3 * b + 3);
+                advance(d0);
+                if (left > 1) advance(d1);
+                if (left > 2) advance(d2);
             }
         }
 
@@ -310,6 +289,11 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 }
 
 // ---- host side ---------------------------------------------------------------
+
+// trajectory mode: capping registers for a third resident 256-thread block costs more re-materialisation (LDC, LEA)
+// than the occupancy returns (374 vs 311 loop instructions): no cap, the host picks 128-thread blocks instead
+template <typename real>
+constexpr int kTrajMinBlocks = 1;
 
 template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1>
 static cudaError_t launch_one(const FusedConsts<real> &c, const LaunchShape &s, ReduceWorkspace ws,
@@ -346,7 +330,7 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
                      : (const void *)heston_fused_kernel<real, 1, false, false, true, 1, 10, 2>);
         return cudaLaunchKernel(fn, dim3(s.blocks), dim3(s.threads), args, 0, stream);
     }
-    if (d_traj != nullptr) return launch_one<real, 4, true, true, true, 2>(c, s, ws, d_x, d_v, d_traj, stream);
+    if (d_traj != nullptr) return launch_one<real, 1, true, true, true, kTrajMinBlocks<real>>(c, s, ws, d_x, d_v, d_traj, stream);
     if constexpr (sizeof(real) == 4) {
         if (!multi && s.variant > 0) {
             void *args[] = {(void *)&c, (void *)&ws, (void *)&d_x, (void *)&d_v, (void *)&d_traj};
@@ -383,7 +367,7 @@ cudaError_t fused_occupancy(int threads, int ppt, bool multi, int variant, int *
     if (ppt == 1) fn = multi ? (const void *)heston_fused_kernel<real, 1, true, false> : (const void *)heston_fused_kernel<real, 1, false, false>;
     else if (ppt == 2) fn = multi ? (const void *)heston_fused_kernel<real, 2, true, false> : (const void *)heston_fused_kernel<real, 2, false, false>;
     else if (ppt == 4) fn = multi ? (const void *)heston_fused_kernel<real, 4, true, false> : (const void *)heston_fused_kernel<real, 4, false, false>;
-    else if (ppt == -4) fn = (const void *)heston_fused_kernel<real, 4, true, true, true, 2>;
+    else if (ppt == -1) fn = (const void *)heston_fused_kernel<real, 1, true, true, true, kTrajMinBlocks<real>>;   // trajectory mode
     else return cudaErrorInvalidValue;
     cudaFuncAttributes attr;
     cudaError_t e = cudaFuncGetAttributes(&attr, fn);

@@ -13,8 +13,11 @@ from cocos_b200.numerics._array import empty_on  # noqa: E402
 R = int(float(sys.argv[1])) if len(sys.argv) > 1 else 4_000_000
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 101
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+threads = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 device.init(device_id=0)
 ctx = device.current_context()
+if threads:
+    ctx.set_launch(threads, 0, 0)
 L = _lib.lib()
 HP = _lib.HestonParams(1.0, math.log(1.0319), 6.21, 0.019, 0.61, -0.7, 0.0, 0.101 ** 2)
 pairs = (R + 1) // 2
