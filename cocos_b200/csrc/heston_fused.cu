@@ -330,7 +330,9 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
                      : (const void *)heston_fused_kernel<real, 1, false, false, true, 1, 10, 2>);
         return cudaLaunchKernel(fn, dim3(s.blocks), dim3(s.threads), args, 0, stream);
     }
-    if (d_traj != nullptr) return launch_one<real, 1, true, true, true, kTrajMinBlocks<real>>(c, s, ws, d_x, d_v, d_traj, stream);
+    if (d_traj != nullptr)
+        return multi ? launch_one<real, 1, true, true, true, kTrajMinBlocks<real>>(c, s, ws, d_x, d_v, d_traj, stream)
+                     : launch_one<real, 1, false, true, true, kTrajMinBlocks<real>>(c, s, ws, d_x, d_v, d_traj, stream);
     if constexpr (sizeof(real) == 4) {
         if (!multi && s.variant > 0) {
             void *args[] = {(void *)&c, (void *)&ws, (void *)&d_x, (void *)&d_v, (void *)&d_traj};
@@ -367,7 +369,9 @@ cudaError_t fused_occupancy(int threads, int ppt, bool multi, int variant, int *
     if (ppt == 1) fn = multi ? (const void *)heston_fused_kernel<real, 1, true, false> : (const void *)heston_fused_kernel<real, 1, false, false>;
     else if (ppt == 2) fn = multi ? (const void *)heston_fused_kernel<real, 2, true, false> : (const void *)heston_fused_kernel<real, 2, false, false>;
     else if (ppt == 4) fn = multi ? (const void *)heston_fused_kernel<real, 4, true, false> : (const void *)heston_fused_kernel<real, 4, false, false>;
-    else if (ppt == -1) fn = (const void *)heston_fused_kernel<real, 1, true, true, true, kTrajMinBlocks<real>>;   // trajectory mode
+    else if (ppt == -1)   // trajectory mode
+        fn = multi ? (const void *)heston_fused_kernel<real, 1, true, true, true, kTrajMinBlocks<real>>
+                   : (const void *)heston_fused_kernel<real, 1, false, true, true, kTrajMinBlocks<real>>;
     else return cudaErrorInvalidValue;
     cudaFuncAttributes attr;
     cudaError_t e = cudaFuncGetAttributes(&attr, fn);
