@@ -228,19 +228,18 @@ def price_path_dependent(x0, v0, r, rho, sigma_v, kappa, v_bar, T, K, nT, R, kin
     p = _params(T, r, kappa, v_bar, sigma_v, rho, x0, v0)
     spec = _lib.PayoffSpec(PAYOFF_KINDS[kind], int(option == "put"), float(barrier or 0.0))
     seed, sub = _random.get_seed(), _random.next_subsequence()
-    L = _lib.lib()
-    launch = getattr(L, f"cb_heston_payoff_launch_{_suffix(dtype)}")
-    k_arr, nK = _lib.strikes_array(strikes)
-    pairs = (R + 1) // 2
+    sfx = _suffix(dtype)
     if compute_device_pool is None:
         ctx = current_context()
-        _lib.check(launch(ctx.handle, ctypes.byref(p), R, nT, k_arr, nK, seed, sub, 0, pairs, None, ctypes.byref(spec)))
+        L = _lib.lib()
+        k_arr, nK = _lib.strikes_array(strikes)
+        launch = getattr(L, f"cb_heston_payoff_launch_{sfx}")
+        _lib.check(launch(ctx.handle, ctypes.byref(p), R, nT, k_arr, nK, seed, sub, 0, (R + 1) // 2, None,
+                          ctypes.byref(spec)))
         sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
         _lib.check(L.cb_heston_price_finish(ctx.handle, nK, sums, sumsq))
     else:
-        def shard_launch(ctx_h, params, R_, N_, k, nk, sd, sb, first, count, comm, dx, dv, dtraj):
-            return launch(ctx_h, params, R_, N_, k, nk, sd, sb, first, count, comm, ctypes.byref(spec))
-        sums, sumsq = compute_device_pool.heston_sums(p, R, nT, strikes, seed, sub, _suffix(dtype), launcher=shard_launch)
+        sums, sumsq = compute_device_pool.heston_sums(p, R, nT, strikes, seed, sub, sfx, spec=spec)
     price, se = _price_from_sums(r, T, R, list(sums), list(sumsq))
     if isinstance(K, (list, tuple, np.ndarray)):
         return price, se

@@ -157,39 +157,35 @@ class ComputeDevicePool:
 
     def heston_sums(self, params: "_lib.HestonParams", R: int, N: int, strikes, seed: int, subsequence: int,
                     dtype_suffix: str = "f32", scheme: str = "euler",
-                    launcher=None) -> tp.Tuple[tp.List[float], tp.List[float]]:
+                    spec: tp.Optional["_lib.PayoffSpec"] = None) -> tp.Tuple[tp.List[float], tp.List[float]]:
         """Shard ceil(R/2) antithetic pairs over the pool; one NCCL allreduce; returns (sums, sumsq).
-        ``launcher`` (same argument list as cb_heston_price_launch_*) substitutes another fused entry point."""
+        ``spec`` selects a path-dependent (or put) payoff of the Euler kernel."""
         L = _lib.lib()
         k_arr, nK = _lib.strikes_array(strikes)
         sums = (ctypes.c_double * nK)()
         sumsq = (ctypes.c_double * nK)()
         G = self.number_of_devices
         comms = self._communicators()
-        if launcher is None and scheme == "euler":
+        if scheme == "euler":
             # the whole job in one C call: shards, launches, grouped allreduce, one host read
             ctxs, comm_arr = self._handle_arrays(comms)
             multi = getattr(L, f"cb_heston_price_multi_{dtype_suffix}")
-            _lib.check(multi(G, ctxs, comm_arr, ctypes.byref(params), R, N, k_arr, nK, seed, subsequence, None, sums,
-                             sumsq))
+            _lib.check(multi(G, ctxs, comm_arr, ctypes.byref(params), R, N, k_arr, nK, seed, subsequence,
+                             ctypes.byref(spec) if spec is not None else None, sums, sumsq))
             return list(sums), list(sumsq)
-        if launcher is not None:
-            launch = launcher
-        elif scheme == "conditional":
-            raw = L.cb_heston_price_conditional_launch_f32
-
-            def launch(ctx_h, p, R_, N_, k, nk, sd, sub, first, count, comm, dx, dv, dtraj):
-                return raw(ctx_h, p, R_, N_, k, nk, sd, sub, first, count, comm, dx, dv)
-        else:
+        if scheme != "conditional":
             raise ValueError(f"unknown scheme {scheme!r}")
+        if spec is not None or dtype_suffix != "f32":
+            raise TypeError("the conditional scheme prices European calls in float32 only")
         pairs = (R + 1) // 2
         if comms is not None:
             _lib.check(L.cb_group_start())
         try:
             for g, ctx in enumerate(self._contexts):
                 first, count = shard_range(pairs, G, g)
-                _lib.check(launch(ctx.handle, ctypes.byref(params), R, N, k_arr, nK, seed, subsequence, first, count,
-                                  comms[g] if comms is not None else None, None, None, None))
+                _lib.check(L.cb_heston_price_conditional_launch_f32(
+                    ctx.handle, ctypes.byref(params), R, N, k_arr, nK, seed, subsequence, first, count,
+                    comms[g] if comms is not None else None, None, None))
         finally:
             if comms is not None:
                 _lib.check(L.cb_group_end())
