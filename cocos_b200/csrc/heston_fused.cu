@@ -226,7 +226,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 #pragma unroll
             for (int q = 0; q < PPT; ++q) cur[q] = rng[q].template block<ROUNDS>(0u, keys);
             uint64_t m1b = 0;                                   // M1 * (index of the block being prefetched)
-#pragma unroll((MINB == 1 || TRAJ) ? 2 : 1)
+#pragma unroll((MINB == 1 || MINB == 3 || TRAJ) ? 2 : 1)
             for (uint32_t b = 0; b < calls; ++b) {
                 uint4 nxt[PPT];
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
@@ -295,6 +295,10 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 template <typename real>
 constexpr int kTrajMinBlocks = 1;
 
+// float strike sweep, one pair per thread: 85 registers uncapped = two resident 256-thread blocks; capped at 80 = three
+template <typename real>
+constexpr int kSweepMinBlocks = sizeof(real) == 4 ? 3 : 1;
+
 template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1>
 static cudaError_t launch_one(const FusedConsts<real> &c, const LaunchShape &s, ReduceWorkspace ws,
                               real *d_x, real *d_v, real *d_traj, cudaStream_t stream) {
@@ -342,7 +346,7 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
     }
     switch (s.pairs_per_thread) {
         case 1:
-            return multi ? launch_one<real, 1, true, false>(c, s, ws, d_x, d_v, nullptr, stream)
+            return multi ? launch_one<real, 1, true, false, true, kSweepMinBlocks<real>>(c, s, ws, d_x, d_v, nullptr, stream)
                          : launch_one<real, 1, false, false>(c, s, ws, d_x, d_v, nullptr, stream);
         case 2:
             return multi ? launch_one<real, 2, true, false>(c, s, ws, d_x, d_v, nullptr, stream)
@@ -366,7 +370,7 @@ cudaError_t fused_occupancy(int threads, int ppt, bool multi, int variant, int *
         if (regs) *regs = a.numRegs;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
     }
-    if (ppt == 1) fn = multi ? (const void *)heston_fused_kernel<real, 1, true, false> : (const void *)heston_fused_kernel<real, 1, false, false>;
+    if (ppt == 1) fn = multi ? (const void *)heston_fused_kernel<real, 1, true, false, true, kSweepMinBlocks<real>> : (const void *)heston_fused_kernel<real, 1, false, false>;
     else if (ppt == 2) fn = multi ? (const void *)heston_fused_kernel<real, 2, true, false> : (const void *)heston_fused_kernel<real, 2, false, false>;
     else if (ppt == 4) fn = multi ? (const void *)heston_fused_kernel<real, 4, true, false> : (const void *)heston_fused_kernel<real, 4, false, false>;
     else if (ppt == -1)   // trajectory mode

@@ -5,7 +5,7 @@
 //
 // Per thread: f64 accumulators of sum(payoff) and sum(antithetic-unit average ^2) -- one strike, or (MULTI) the
 // lane-transposed sweep in which lane l keeps strikes l and l+32 for its whole warp and terminal prices are
-// broadcast by shuffle.  Per block: warp shuffles / shared memory -> partials[block].  The last block to arrive
+// broadcast by shuffle (2 shuffles + 2 x ~10 instructions per source lane).  Per block: warp shuffles / shared memory -> partials[block].  The last block to arrive
 // (atomic ticket) folds the partials in block order into ws.result, so a launch is bit-reproducible, and resets
 // the ticket for the next launch on the stream.  ws.result is also the NCCL send/receive buffer.
 #pragma once
@@ -34,22 +34,37 @@ struct PayoffAccumulator {
             sum[0] += tot;
             sq[0] = fma(unit, unit, sq[0]);
         } else {
-            const real m1 = active ? (real)1 : (real)0;
-            const real m2 = paired ? (real)1 : (real)0;
-            for (int src = 0; src < 32; ++src) {
-                const real s1 = __shfl_sync(0xffffffffu, S1, src);
-                const real s2 = __shfl_sync(0xffffffffu, S2, src);
-                const real g1 = __shfl_sync(0xffffffffu, m1, src);
-                const real g2 = __shfl_sync(0xffffffffu, m2, src);
+            // dead lanes carry -inf so that max(. - K, 0) vanishes for every strike: no mask travels with the prices.
+            // sq collects (2 * unit average)^2 = (p1 + p2)^2 -- publish() scales by 1/4, exactly.  Only the lone
+            // unpaired path of an odd R (one warp of the whole simulation) needs the factor 2 and takes the slow loop.
+            const real dead = -(real)INFINITY;
+            const real a1 = active ? sign * S1 : dead;
+            const real a2 = paired ? sign * S2 : dead;
+            const real sK[2] = {sign * s_strikes[lane], sign * s_strikes[lane + 32]};
+            const bool lone = active && !paired;
+            if (!__any_sync(0xffffffffu, lone)) {
+                for (int src = 0; src < 32; ++src) {
+                    const real s1 = __shfl_sync(0xffffffffu, a1, src);
+                    const real s2 = __shfl_sync(0xffffffffu, a2, src);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const real K = s_strikes[lane + 32 * h];
-                    const real p1 = g1 * fmax(sign * (s1 - K), (real)0);
-                    const real p2 = g2 * fmax(sign * (s2 - K), (real)0);
-                    const double tot = (double)(p1 + p2);
-                    const double unit = tot * (0.5 + 0.5 * (double)(g1 - g2));   // 0.5*tot if paired, tot if single
-                    sum[h] += tot;
-                    sq[h] = fma(unit, unit, sq[h]);
+                    for (int h = 0; h < 2; ++h) {
+                        const double tot = (double)(fmax(s1 - sK[h], (real)0) + fmax(s2 - sK[h], (real)0));
+                        sum[h] += tot;
+                        sq[h] = fma(tot, tot, sq[h]);
+                    }
+                }
+            } else {
+                const real f = lone ? (real)2 : (real)1;
+                for (int src = 0; src < 32; ++src) {
+                    const real s1 = __shfl_sync(0xffffffffu, a1, src);
+                    const real s2 = __shfl_sync(0xffffffffu, a2, src);
+                    const double twice = (double)__shfl_sync(0xffffffffu, f, src);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double tot = (double)(fmax(s1 - sK[h], (real)0) + fmax(s2 - sK[h], (real)0));
+                        sum[h] += tot;
+                        sq[h] = fma(twice * tot, twice * tot, sq[h]);
+                    }
                 }
             }
         }
@@ -70,7 +85,7 @@ struct PayoffAccumulator {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int k = lane + 32 * h;
-                if (k < nK) { s_acc[warp][k] = sum[h]; s_acc[warp][nK + k] = sq[h]; }
+                if (k < nK) { s_acc[warp][k] = sum[h]; s_acc[warp][nK + k] = 0.25 * sq[h]; }
             }
         }
         __syncthreads();
