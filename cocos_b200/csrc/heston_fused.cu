@@ -226,7 +226,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 #pragma unroll
             for (int q = 0; q < PPT; ++q) cur[q] = rng[q].template block<ROUNDS>(0u, keys);
             uint64_t m1b = 0;                                   // M1 * (index of the block being prefetched)
-#pragma unroll((MINB == 1 || MINB == 3 || TRAJ) ? 2 : 1)
+#pragma unroll((MINB == 1 || MINB == 3 || TRAJ || sizeof(real) == 8) ? 2 : 1)
             for (uint32_t b = 0; b < calls; ++b) {
                 uint4 nxt[PPT];
                 StepDraw d0[PPT], d1[PPT], d2[PPT];
@@ -299,6 +299,11 @@ constexpr int kTrajMinBlocks = 1;
 template <typename real>
 constexpr int kSweepMinBlocks = sizeof(real) == 4 ? 3 : 1;
 
+// double, two pairs per thread, one strike: capped at 128 registers (two 256-thread blocks' worth) four 128-thread
+// blocks are resident instead of three (+2%); the strike sweep spills under the same cap and stays uncapped
+template <typename real>
+constexpr int kTwoPairMinBlocks = sizeof(real) == 8 ? 2 : 1;
+
 template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1>
 static cudaError_t launch_one(const FusedConsts<real> &c, const LaunchShape &s, ReduceWorkspace ws,
                               real *d_x, real *d_v, real *d_traj, cudaStream_t stream) {
@@ -350,7 +355,7 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
                          : launch_one<real, 1, false, false>(c, s, ws, d_x, d_v, nullptr, stream);
         case 2:
             return multi ? launch_one<real, 2, true, false>(c, s, ws, d_x, d_v, nullptr, stream)
-                         : launch_one<real, 2, false, false>(c, s, ws, d_x, d_v, nullptr, stream);
+                         : launch_one<real, 2, false, false, true, kTwoPairMinBlocks<real>>(c, s, ws, d_x, d_v, nullptr, stream);
         case 4:
             return multi ? launch_one<real, 4, true, false>(c, s, ws, d_x, d_v, nullptr, stream)
                          : launch_one<real, 4, false, false>(c, s, ws, d_x, d_v, nullptr, stream);
@@ -371,7 +376,7 @@ cudaError_t fused_occupancy(int threads, int ppt, bool multi, int variant, int *
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
     }
     if (ppt == 1) fn = multi ? (const void *)heston_fused_kernel<real, 1, true, false, true, kSweepMinBlocks<real>> : (const void *)heston_fused_kernel<real, 1, false, false>;
-    else if (ppt == 2) fn = multi ? (const void *)heston_fused_kernel<real, 2, true, false> : (const void *)heston_fused_kernel<real, 2, false, false>;
+    else if (ppt == 2) fn = multi ? (const void *)heston_fused_kernel<real, 2, true, false> : (const void *)heston_fused_kernel<real, 2, false, false, true, kTwoPairMinBlocks<real>>;
     else if (ppt == 4) fn = multi ? (const void *)heston_fused_kernel<real, 4, true, false> : (const void *)heston_fused_kernel<real, 4, false, false>;
     else if (ppt == -1)   // trajectory mode
         fn = multi ? (const void *)heston_fused_kernel<real, 1, true, true, true, kTrajMinBlocks<real>>
