@@ -284,10 +284,14 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C3 Heston European call, 10M paths x 500 steps fp32, fused in-kernel Philox"
-                                   + (f", x{world} GPUs sharded by antithetic pair range + 1 NCCL allreduce/step"
+                                   + (f", x{world} GPUs sharded by antithetic pair range, cross-GPU sum "
+                                      + ("fused into the kernel over NVLink peer memory" if pricer.peer_exchange
+                                         else "by 1 NCCL allreduce/step")
                                       if world > 1 else ", single B200"),
                        "paths": R, "paths_per_gpu": PATHS_PER_GPU, "nT": N_T, "antithetic": True,
                        "parallelism": f"pair-shard x{world}",
+                       "collective": ("none" if world == 1 else
+                                      "fused-peer-exchange" if pricer.peer_exchange else "nccl-allreduce"),
                        "l2": "256 MiB memset between timed steps (the kernel itself reads no memory input)",
                        "launch": {"threads": args.threads, "blocks_per_sm": args.blocks_per_sm, "ppt": args.ppt}},
             "price": float(price[0]), "price_se": float(se[0]),

@@ -17,6 +17,7 @@ P = ctypes.POINTER
 
 MAX_STRIKES = 64
 UNIQUE_ID_BYTES = 128
+P2P_HANDLE_BYTES = 64
 
 CB_OK, CB_ERR_INVALID, CB_ERR_CUDA, CB_ERR_NCCL, CB_ERR_UNSUPPORTED = range(5)
 
@@ -96,6 +97,10 @@ PROTOTYPES = {
     "cb_comm_init_rank": (c_int, [c_void_p, c_int, c_int, c_void_p, P(c_void_p)]),
     "cb_comm_init_all": (c_int, [c_int, P(c_void_p), P(c_void_p)]),
     "cb_comm_destroy": (c_int, [c_void_p]),
+    "cb_comm_p2p_export": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cb_comm_p2p_import": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cb_comm_p2p_enable": (c_int, [c_void_p, c_int]),
+    "cb_comm_p2p_active": (c_int, [c_void_p, P(c_int)]),
     "cb_allreduce_sum_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_size]),
     "cb_group_start": (c_int, []),
     "cb_group_end": (c_int, []),

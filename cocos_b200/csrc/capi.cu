@@ -65,6 +65,13 @@ struct cb_ctx {
 struct cb_comm {
     ncclComm_t comm = nullptr;
     int nranks = 0, rank = 0;
+    // fused peer exchange (PeerExchange in kernels.h): this rank's buffer, the peers' mappings, the launch counter
+    int dev = -1;
+    void *xchg = nullptr;                 // owned: kExchangeBytes on `dev`
+    void *imported[kMaxPeers] = {};       // cudaIpcOpenMemHandle mappings (other processes' buffers)
+    PeerExchange px = {};
+    bool p2p = false;
+    unsigned int epoch = 0;
 };
 
 extern "C" CB_API const char *cb_last_error(void) { return g_err; }
@@ -342,6 +349,110 @@ extern "C" CB_API int cb_comm_unique_id(void *h_id) {
     return CB_OK;
 }
 
+// ---- fused peer exchange: set-up ------------------------------------------------------------------------------
+
+static void exchange_point(cb_comm *m, int peer, void *base) {
+    m->px.slots[peer] = reinterpret_cast<double *>(base);
+    m->px.flags[peer] = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(base) + kExchangeSlotBytes);
+}
+
+static int exchange_allocate(cb_comm *m, int dev) {
+    CB_CUDA(cudaSetDevice(dev));
+    m->dev = dev;
+    CB_CUDA(cudaMalloc(&m->xchg, kExchangeBytes));
+    CB_CUDA(cudaMemset(m->xchg, 0, kExchangeBytes));
+    CB_CUDA(cudaDeviceSynchronize());
+    m->px.nranks = m->nranks;
+    m->px.rank = m->rank;
+    exchange_point(m, m->rank, m->xchg);
+    return CB_OK;
+}
+
+static void exchange_release(cb_comm *m) {
+    if (m->dev >= 0) cudaSetDevice(m->dev);
+    for (int p = 0; p < kMaxPeers; ++p)
+        if (m->imported[p]) cudaIpcCloseMemHandle(m->imported[p]);
+    if (m->xchg) cudaFree(m->xchg);
+    m->xchg = nullptr;
+    m->p2p = false;
+}
+
+// one process, n devices: peer access both ways between every pair, then plain pointers
+static bool exchange_connect_local(int n, cb_ctx *const *ctxs, cb_comm **comms) {
+    if (n < 2 || n > kMaxPeers || getenv("COCOS_B200_NO_P2P") != nullptr) return false;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            if (ctxs[i]->dev == ctxs[j]->dev) return false;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctxs[i]->dev, ctxs[j]->dev) != cudaSuccess || !can) return false;
+        }
+    for (int i = 0; i < n; ++i) {
+        if (cudaSetDevice(ctxs[i]->dev) != cudaSuccess) return false;
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->dev, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { cudaGetLastError(); return false; }
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        if (exchange_allocate(comms[i], ctxs[i]->dev) != CB_OK) return false;
+    for (int i = 0; i < n; ++i) {
+        for (int p = 0; p < n; ++p) exchange_point(comms[i], p, comms[p]->xchg);
+        comms[i]->p2p = true;
+    }
+    return true;
+}
+
+extern "C" CB_API int cb_comm_p2p_export(cb_ctx *c, cb_comm *m, void *h_handle) {
+    CB_CTX(c);
+    CB_REQUIRE(m != nullptr && h_handle != nullptr, "NULL argument");
+    CB_REQUIRE(m->nranks >= 2 && m->nranks <= kMaxPeers, "the fused exchange serves 2..%d ranks", kMaxPeers);
+    static_assert(sizeof(cudaIpcMemHandle_t) == CB_P2P_HANDLE_BYTES, "ipc handle size");
+    if (m->xchg == nullptr) {
+        int rc = exchange_allocate(m, c->dev);
+        if (rc) return rc;
+    }
+    cudaIpcMemHandle_t h;
+    CB_CUDA(cudaIpcGetMemHandle(&h, m->xchg));
+    memcpy(h_handle, &h, sizeof h);
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_comm_p2p_import(cb_ctx *c, cb_comm *m, const void *h_handles) {
+    CB_CTX(c);
+    CB_REQUIRE(m != nullptr && h_handles != nullptr, "NULL argument");
+    CB_REQUIRE(m->xchg != nullptr, "cb_comm_p2p_export comes first");
+    for (int p = 0; p < m->nranks; ++p) {
+        if (p == m->rank || m->imported[p] != nullptr) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(h_handles) + (size_t)p * sizeof h, sizeof h);
+        void *base = nullptr;
+        CB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        m->imported[p] = base;
+        exchange_point(m, p, base);
+    }
+    return CB_OK;
+}
+
+// All ranks must agree: enable only after EVERY rank imported successfully (the host side checks that).
+extern "C" CB_API int cb_comm_p2p_enable(cb_comm *m, int enable) {
+    CB_REQUIRE(m != nullptr, "comm is NULL");
+    if (enable) {
+        CB_REQUIRE(m->xchg != nullptr, "no exchange buffer: export/import first");
+        for (int p = 0; p < m->nranks; ++p) CB_REQUIRE(m->px.slots[p] != nullptr, "rank %d is not mapped", p);
+    }
+    m->p2p = enable != 0;
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_comm_p2p_active(const cb_comm *m, int *active) {
+    CB_REQUIRE(m != nullptr && active != nullptr, "NULL argument");
+    *active = m->p2p ? 1 : 0;
+    return CB_OK;
+}
+
 extern "C" CB_API int cb_comm_init_rank(cb_ctx *c, int nranks, int rank, const void *h_id, cb_comm **out) {
     CB_CTX(c);
     CB_REQUIRE(out != nullptr && h_id != nullptr, "NULL argument");
@@ -380,11 +491,14 @@ extern "C" CB_API int cb_comm_init_all(int n, cb_ctx *const *ctxs, cb_comm **out
         out[i]->nranks = n;
         out[i]->rank = i;
     }
+    if (!exchange_connect_local(n, ctxs, out))              // no peer access: the NCCL allreduce stays in the path
+        for (int i = 0; i < n; ++i) exchange_release(out[i]);
     return CB_OK;
 }
 
 extern "C" CB_API int cb_comm_destroy(cb_comm *m) {
     if (m == nullptr) return CB_OK;
+    exchange_release(m);
     if (g_nccl.ok && m->comm) g_nccl.CommDestroy(m->comm);
     delete m;
     return CB_OK;
@@ -669,6 +783,14 @@ extern "C" CB_API int cb_heston_terminal_injected_host_f32(cb_ctx *c, const floa
 
 // ---------------------------------------------------------------- Heston: fused kernel
 
+// hands the kernel this launch's view of the communicator's peer mappings; false = no fused exchange
+static bool exchange_arm(cb_comm *comm, ReduceWorkspace *ws) {
+    if (comm == nullptr || !comm->p2p) return false;
+    ws->px = comm->px;
+    ws->px.epoch = ++comm->epoch;
+    return true;
+}
+
 template <typename real>
 static FusedConsts<real> make_consts(const cb_heston_params *p, uint64_t R, uint32_t N, const double *strikes, int nK,
                                      uint64_t seed, uint32_t subsequence, uint64_t pair_first, uint64_t pair_count) {
@@ -778,17 +900,21 @@ static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R,
             k.barrier_log = (real)(sgn * std::log(spec->barrier));
         }
     }
-    if (pair_count > 0) {
+    // the cross-GPU sum: fused into the kernel's last block over NVLink peer mappings when the communicator has
+    // them (an empty shard still launches one block to publish its zeros), else one ncclAllReduce behind the kernel
+    ReduceWorkspace ws = c->ws;
+    const bool fused_exchange = exchange_arm(comm, &ws);
+    if (pair_count > 0 || fused_exchange) {
         LaunchShape shape;
         rc = choose_shape<real>(c, pair_count, nK > 1, d_traj != nullptr, &shape);
         if (rc) return rc;
         if (k.payoff_kind != 0 || k.payoff_sign < (real)0) shape.variant = 0;
         if (k.payoff_kind != 0) shape.pairs_per_thread = 1;
-        CB_CUDA(launch_heston_fused<real>(k, shape, c->ws, d_x, d_v, d_traj, c->stream));
+        CB_CUDA(launch_heston_fused<real>(k, shape, ws, d_x, d_v, d_traj, c->stream));
     } else {
         CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));   // an empty shard adds nothing
     }
-    if (comm != nullptr)
+    if (comm != nullptr && !fused_exchange)
         CB_NCCL(g_nccl.AllReduce(c->ws.result, c->ws.result, (size_t)2 * nK, ncclDouble, ncclSum, comm->comm,
                                  c->stream));
     return CB_OK;
@@ -846,13 +972,15 @@ extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb
         if (rc) return rc;
     }
     const FusedConsts<float> k = make_consts<float>(p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count);
-    if (pair_count > 0) {
+    ReduceWorkspace ws = c->ws;
+    const bool fused_exchange = exchange_arm(comm, &ws);
+    if (pair_count > 0 || fused_exchange) {
         const int threads = c->threads ? c->threads : 256;
         int bps = 0;
         CB_CUDA(conditional_occupancy(threads, nK > 1, &bps));
         CB_REQUIRE(bps >= 1, "kernel does not fit");
         if (c->blocks_per_sm > 0) bps = std::min(bps, c->blocks_per_sm);
-        const uint64_t items = (pair_count + threads - 1) / threads;
+        const uint64_t items = std::max<uint64_t>(1, (pair_count + threads - 1) / threads);
         uint64_t blocks = std::min<uint64_t>(items, (uint64_t)c->sm_count * bps);
         if (items > blocks) {                              // same wave-aware choice as choose_shape
             double best = -1.0;
@@ -864,12 +992,12 @@ extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb
         }
         blocks = std::min<uint64_t>(blocks, kMaxGridBlocks);
         const double dt = p->T / (double)(N - 1);
-        CB_CUDA(launch_heston_conditional(k, (float)p->sigma_v, (float)p->rho, (float)dt, threads, (int)blocks, c->ws,
+        CB_CUDA(launch_heston_conditional(k, (float)p->sigma_v, (float)p->rho, (float)dt, threads, (int)blocks, ws,
                                           d_x, d_v, c->stream));
     } else {
         CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));
     }
-    if (comm != nullptr)
+    if (comm != nullptr && !fused_exchange)
         CB_NCCL(g_nccl.AllReduce(c->ws.result, c->ws.result, (size_t)2 * nK, ncclDouble, ncclSum, comm->comm,
                                  c->stream));
     return CB_OK;
@@ -881,6 +1009,10 @@ extern "C" CB_API int cb_heston_price_finish(cb_ctx *c, int nK, double *h_sum, d
     CB_REQUIRE(h_sum != nullptr && h_sumsq != nullptr, "NULL output");
     CB_CUDA(cudaMemcpyAsync(c->h_result, c->ws.result, sizeof(double) * 2 * nK, cudaMemcpyDeviceToHost, c->stream));
     CB_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long first_bits;
+    memcpy(&first_bits, c->h_result, sizeof first_bits);
+    if (first_bits == kExchangeTimeoutBits)
+        return fail(CB_ERR_CUDA, "fused peer exchange timed out: a rank of the communicator never launched its shard");
     memcpy(h_sum, c->h_result, sizeof(double) * nK);
     memcpy(h_sumsq, c->h_result + nK, sizeof(double) * nK);
     return CB_OK;

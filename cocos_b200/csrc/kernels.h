@@ -47,10 +47,29 @@ struct FusedConsts {
     real strikes[kMaxStrikes];
 };
 
+// Cross-GPU reduction fused into the simulation kernel (no collective library in the data path): the last block of
+// every rank writes its totals into slot [epoch parity][rank] of EVERY rank's exchange buffer through NVLink peer
+// mappings, raises its flag there (release, system scope), waits until all ranks' flags have arrived on its own
+// device (acquire) and folds the slots in rank order -- every rank ends with the same bits in `result`.
+// Two slot parities make the next launch's writes safe: a rank can only be one launch ahead of the slowest one.
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+    int nranks;                       // < 2: no exchange
+    int rank;
+    unsigned int epoch;               // launch number on this communicator (> 0), identical on every rank
+    double *slots[kMaxPeers];         // rank p's buffer, mapped here: [2][kMaxPeers][kMaxAcc]
+    unsigned int *flags[kMaxPeers];   // rank p's flags, mapped here: [kMaxPeers], flags[r] = last epoch published by r
+};
+constexpr size_t kExchangeSlotBytes = sizeof(double) * 2 * kMaxPeers * kMaxAcc;
+constexpr size_t kExchangeBytes = kExchangeSlotBytes + sizeof(unsigned int) * kMaxPeers;
+// what `result` holds when a peer never showed up (a quiet NaN with a recognisable payload)
+constexpr unsigned long long kExchangeTimeoutBits = 0x7FF8C0C05B200DEAull;
+
 struct ReduceWorkspace {
     double *partials;    // [kMaxGridBlocks][kMaxAcc]
     unsigned int *ticket;
     double *result;      // [kMaxAcc]: sums[nK] then sumsq[nK]
+    PeerExchange px;
 };
 
 template <typename real>

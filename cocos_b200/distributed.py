@@ -1,12 +1,15 @@
 """One-process-per-GPU sharding of the Heston path (``torchrun`` / ``torch.distributed`` launch).
 
 ``torch.distributed`` is plumbing only: rendezvous, the broadcast of the NCCL unique
-id, barriers and the max-over-ranks of timings.  The data path has exactly one
-collective -- the ``ncclAllReduce`` of the 2*nK payoff sums that
-``cb_heston_price_launch_*`` issues on the kernel's own stream -- and every rank
-simulates a disjoint, contiguous block of antithetic pairs from a disjoint Philox
-counter range, so prices do not depend on the number of GPUs (up to fp64 summation
-order).  Stands in for the process pool of cocos/multi_processing/device_pool.py:103-128.
+id and of the CUDA IPC handles, barriers and the max-over-ranks of timings.  The data
+path has exactly one exchange -- the sum of the 2*nK payoff totals -- and it runs
+INSIDE the simulation kernel: every rank's last block writes its totals into every
+rank's exchange buffer over NVLink peer mappings and folds them in rank order
+(``PeerExchange``, csrc/kernels.h).  Where peer mappings cannot be made, one
+``ncclAllReduce`` on the kernel's stream does the same.  Every rank simulates a
+disjoint, contiguous block of antithetic pairs from a disjoint Philox counter range, so
+prices do not depend on the number of GPUs (up to fp64 summation order).  Stands in for
+the process pool of cocos/multi_processing/device_pool.py:103-128.
 """
 import ctypes
 import math
@@ -45,10 +48,12 @@ def broadcast_unique_id(group=None) -> bytes:
 class ShardedPricer:
     """Rank-local handle: context on this rank's GPU plus its NCCL communicator."""
 
-    def __init__(self, device: int, rank: int, world_size: int, unique_id: tp.Optional[bytes] = None):
+    def __init__(self, device: int, rank: int, world_size: int, unique_id: tp.Optional[bytes] = None,
+                 peer_exchange: bool = True, group=None):
         self.rank, self.world_size = rank, world_size
         self.ctx = _lib.context(device)
         self.comm = None
+        self.peer_exchange = False
         if world_size > 1:
             if unique_id is None or len(unique_id) != _lib.UNIQUE_ID_BYTES:
                 raise ValueError("a 128-byte NCCL unique id is required when world_size > 1")
@@ -56,6 +61,29 @@ class ShardedPricer:
             _lib.check(_lib.lib().cb_comm_init_rank(self.ctx.handle, world_size, rank, unique_id,
                                                     ctypes.byref(handle)))
             self.comm = handle
+            if peer_exchange and "COCOS_B200_NO_P2P" not in os.environ:
+                self.peer_exchange = self._connect_peers(group)
+
+    def _connect_peers(self, group) -> bool:
+        """Exchange CUDA IPC handles of the ranks' exchange buffers; all ranks enable the fused exchange or none."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or self.world_size > 8:
+            return False
+        L = _lib.lib()
+        buf = ctypes.create_string_buffer(_lib.P2P_HANDLE_BYTES)
+        mine = bytes(buf.raw) if L.cb_comm_p2p_export(self.ctx.handle, self.comm, buf) == 0 else None
+        if mine is not None:
+            mine = bytes(buf.raw)
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, mine, group=group)
+        ok = all(h is not None for h in handles) and \
+            L.cb_comm_p2p_import(self.ctx.handle, self.comm, b"".join(handles)) == 0
+        votes = [None] * self.world_size
+        dist.all_gather_object(votes, bool(ok), group=group)
+        if not all(votes):
+            return False
+        _lib.check(L.cb_comm_p2p_enable(self.comm, 1))
+        return True
 
     def launch(self, params: "_lib.HestonParams", R: int, nT: int, strikes, seed: int, subsequence: int,
                dtype_suffix: str = "f32", scheme: str = "euler"):

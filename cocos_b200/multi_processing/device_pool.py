@@ -155,6 +155,17 @@ class ComputeDevicePool:
             self._comms = [ctypes.c_void_p(c) for c in comms]
         return self._comms
 
+    @property
+    def peer_exchange_active(self) -> bool:
+        """True when the cross-GPU sum of the fused launches runs inside the kernel over NVLink peer mappings
+        (every device pair has peer access); False: one ncclAllReduce follows each kernel."""
+        comms = self._communicators()
+        if comms is None:
+            return False
+        active = ctypes.c_int(0)
+        _lib.check(_lib.lib().cb_comm_p2p_active(comms[0], ctypes.byref(active)))
+        return bool(active.value)
+
     def heston_sums(self, params: "_lib.HestonParams", R: int, N: int, strikes, seed: int, subsequence: int,
                     dtype_suffix: str = "f32", scheme: str = "euler",
                     spec: tp.Optional["_lib.PayoffSpec"] = None) -> tp.Tuple[tp.List[float], tp.List[float]]:

@@ -62,6 +62,7 @@ typedef struct {
 
 #define CB_MAX_STRIKES 64
 #define CB_UNIQUE_ID_BYTES 128
+#define CB_P2P_HANDLE_BYTES 64
 
 /* ---- library / device management: cocos/device.py:95-205 ---------------- */
 CB_API const char *cb_last_error(void);
@@ -237,6 +238,16 @@ CB_API int cb_comm_unique_id(void *h_id /* CB_UNIQUE_ID_BYTES */);
 CB_API int cb_comm_init_rank(cb_ctx *ctx, int nranks, int rank, const void *h_id, cb_comm **out);
 CB_API int cb_comm_init_all(int n, cb_ctx *const *ctxs, cb_comm **out /* [n] */);   /* one process, n devices */
 CB_API int cb_comm_destroy(cb_comm *comm);
+/* Fused peer exchange: with it the cross-GPU sum of the fused Heston launches runs INSIDE the simulation kernel --
+ * every rank's last block writes its totals into every rank's exchange buffer through NVLink peer mappings and folds
+ * them in rank order -- and no collective follows the kernel.  cb_comm_init_all connects the buffers by itself when
+ * every device pair has peer access.  One process per GPU: each rank exports its buffer as a CUDA IPC handle, the
+ * host gathers the nranks handles (rank order), each rank imports them, and once EVERY rank has succeeded all call
+ * cb_comm_p2p_enable(comm, 1); otherwise the ncclAllReduce stays in the path. */
+CB_API int cb_comm_p2p_export(cb_ctx *ctx, cb_comm *comm, void *h_handle /* CB_P2P_HANDLE_BYTES */);
+CB_API int cb_comm_p2p_import(cb_ctx *ctx, cb_comm *comm, const void *h_handles /* nranks * CB_P2P_HANDLE_BYTES */);
+CB_API int cb_comm_p2p_enable(cb_comm *comm, int enable);
+CB_API int cb_comm_p2p_active(const cb_comm *comm, int *active);
 CB_API int cb_allreduce_sum_f64(cb_ctx *ctx, cb_comm *comm, double *d_buf, size_t count);
 CB_API int cb_group_start(void);
 CB_API int cb_group_end(void);

@@ -88,7 +88,7 @@ def test_pi_sharded_over_pool(gpu_device):
 
 @needs2
 def test_torchrun_bench_two_ranks(golden_values):
-    """bench.py under torchrun: one rank per GPU, NCCL allreduce inside the C library."""
+    """bench.py under torchrun: one rank per GPU, the cross-GPU sum inside the C library (fused or NCCL)."""
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "3",
@@ -102,6 +102,14 @@ def test_torchrun_bench_two_ranks(golden_values):
     ref = golden_values["statistical"]["nT501"]
     assert abs(res["price"] - ref["price"]) <= 3 * math.hypot(res["price_se"], ref["se"])
     assert abs(res["e2e"]["price"] - ref["price"]) <= 3 * math.hypot(res["price_se"], ref["se"])
+    assert res["config"]["collective"] in ("fused-peer-exchange", "nccl-allreduce")
+    # the same job with the fused exchange switched off: same price to the last bits (two ranks: a+b either way)
+    out2 = subprocess.run(cmd[:9] + ["29614"] + cmd[10:] + ["--no-cpu-baseline"], capture_output=True, text=True,
+                          cwd=ROOT, env=dict(env, COCOS_B200_NO_P2P="1"), timeout=600)
+    assert out2.returncode == 0, out2.stderr[-2000:]
+    res2 = json.loads([l for l in out2.stdout.splitlines() if l.startswith("{")][0])
+    assert res2["config"]["collective"] == "nccl-allreduce"
+    assert abs(res2["price"] - res["price"]) <= 1e-12
 
 
 def _multi(G, R, N, strikes, seed, sub, suffix="f32", spec=None):
@@ -188,3 +196,44 @@ def test_nccl_loaded_before_torch_is_the_bundled_copy():
             "print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@needs2
+def test_fused_peer_exchange_equals_nccl_allreduce(gpu_device, ref_params, monkeypatch):
+    """The in-kernel cross-GPU sum over NVLink peer mappings and the NCCL allreduce behind the kernel give the same
+    totals: several launches in a row (both slot parities), float and double, strike sweep, the conditional scheme,
+    a path-dependent payoff and a job so small that one shard is empty."""
+    from cocos_b200 import _lib
+    from cocos_b200.multi_processing import ComputeDevicePool
+    q = ref_params
+    p = _lib.HestonParams(q["T"], q["r"], q["kappa"], q["v_bar"], q["sigma_v"], q["rho"], q["x0"], q["v0"])
+    n = _device_count()
+
+    def run(pool):
+        out = []
+        for sub in range(5):
+            out.append(pool.heston_sums(p, 200_001, 33, [0.95], seed=3, subsequence=sub))
+        out.append(pool.heston_sums(p, 100_000, 33, [0.8, 0.9, 1.0, 1.1], seed=3, subsequence=9))
+        out.append(pool.heston_sums(p, 100_000, 33, [0.8, 0.9, 1.0, 1.1], seed=3, subsequence=9, dtype_suffix="f64"))
+        out.append(pool.heston_sums(p, 100_000, 34, [0.95], seed=3, subsequence=10, scheme="conditional"))
+        out.append(pool.heston_sums(p, 100_000, 33, [0.95], seed=3, subsequence=11, spec=_lib.PayoffSpec(1, 0, 0.0)))
+        out.append(pool.heston_sums(p, 1, 33, [0.95], seed=3, subsequence=12))        # one pair: the other shards are empty
+        out.append(pool.heston_sums(p, 200_001, 33, [0.95], seed=3, subsequence=13))  # and the exchange still lines up
+        return out
+
+    for g in sorted({2, n}):
+        fused_pool = ComputeDevicePool(compute_devices=list(range(g)))
+        if not fused_pool.peer_exchange_active:
+            fused_pool.close()
+            pytest.skip("no peer access between the devices of this box")
+        fused = run(fused_pool)
+        fused_pool.close()
+        monkeypatch.setenv("COCOS_B200_NO_P2P", "1")
+        nccl_pool = ComputeDevicePool(compute_devices=list(range(g)))
+        assert not nccl_pool.peer_exchange_active
+        via_nccl = run(nccl_pool)
+        nccl_pool.close()
+        monkeypatch.delenv("COCOS_B200_NO_P2P")
+        for (s1, q1), (s2, q2) in zip(fused, via_nccl):
+            np.testing.assert_allclose(s1, s2, rtol=1e-13)
+            np.testing.assert_allclose(q1, q2, rtol=1e-13)
