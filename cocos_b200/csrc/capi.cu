@@ -821,9 +821,9 @@ static FusedConsts<real> make_consts(const cb_heston_params *p, uint64_t R, uint
     return k;
 }
 
-// Wave-aware geometry: with W = ceil(pairs / (threads*ppt)) block-sized work items and
-// at most sm*bps resident blocks, pick the residency (>= 60% of the maximum) whose
-// last wave is fullest; every thread then runs the same number of iterations.
+// Geometry: a grid of (resident blocks per SM) x (SM count) blocks, grid-stride over the shard's pairs.  The last
+// round is usually partial: warps that lie wholly past the end skip it (heston_fused_kernel), so its cost is
+// proportional to what is left and the largest residency is always the best choice.
 template <typename real>
 static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, LaunchShape *s) {
     // defaults from the tools/tune_fused.py sweeps: float 256 threads x 1 pair, double 128 threads x 2 pairs
@@ -846,21 +846,8 @@ static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, L
     if (c->blocks_per_sm > 0) {
         // explicit grid: sm_count * blocks_per_sm blocks (more than fit at once => the hardware back-fills)
         blocks = std::min<uint64_t>(items, (uint64_t)c->sm_count * c->blocks_per_sm);
-    } else if (items <= resident) {
-        blocks = items;
     } else {
-        double best = -1.0;
-        blocks = resident;
-        for (int b = bps; b >= std::max(1, (int)std::ceil(0.6 * bps)); --b) {
-            const uint64_t g = (uint64_t)c->sm_count * b;
-            const uint64_t waves = (items + g - 1) / g;
-            // time ~ waves * b (a wave of b blocks/SM takes ~b units once the pipe is saturated)
-            const double eff = (double)items / ((double)waves * (double)g);
-            if (eff > best + 1e-9) {
-                best = eff;
-                blocks = g;
-            }
-        }
+        blocks = std::min(items, resident);
     }
     blocks = std::min<uint64_t>(blocks, kMaxGridBlocks);
     s->threads = threads;
@@ -902,14 +889,16 @@ static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R,
     }
     // the cross-GPU sum: fused into the kernel's last block over NVLink peer mappings when the communicator has
     // them (an empty shard still launches one block to publish its zeros), else one ncclAllReduce behind the kernel
+    // (kernels with the exchange exist for the default geometry of plain pricing launches; the rest keep NCCL)
     ReduceWorkspace ws = c->ws;
-    const bool fused_exchange = exchange_arm(comm, &ws);
+    LaunchShape shape;
+    rc = choose_shape<real>(c, pair_count, nK > 1, d_traj != nullptr, &shape);
+    if (rc) return rc;
+    if (k.payoff_kind != 0 || k.payoff_sign < (real)0) shape.variant = 0;
+    if (k.payoff_kind != 0) shape.pairs_per_thread = 1;
+    const bool fused_exchange = fused_exchange_supported<real>(shape, k.payoff_kind, d_traj != nullptr) &&
+                                exchange_arm(comm, &ws);
     if (pair_count > 0 || fused_exchange) {
-        LaunchShape shape;
-        rc = choose_shape<real>(c, pair_count, nK > 1, d_traj != nullptr, &shape);
-        if (rc) return rc;
-        if (k.payoff_kind != 0 || k.payoff_sign < (real)0) shape.variant = 0;
-        if (k.payoff_kind != 0) shape.pairs_per_thread = 1;
         CB_CUDA(launch_heston_fused<real>(k, shape, ws, d_x, d_v, d_traj, c->stream));
     } else {
         CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));   // an empty shard adds nothing
@@ -982,14 +971,6 @@ extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb
         if (c->blocks_per_sm > 0) bps = std::min(bps, c->blocks_per_sm);
         const uint64_t items = std::max<uint64_t>(1, (pair_count + threads - 1) / threads);
         uint64_t blocks = std::min<uint64_t>(items, (uint64_t)c->sm_count * bps);
-        if (items > blocks) {                              // same wave-aware choice as choose_shape
-            double best = -1.0;
-            for (int b = bps; b >= std::max(1, (int)std::ceil(0.6 * bps)); --b) {
-                const uint64_t g = (uint64_t)c->sm_count * b, waves = (items + g - 1) / g;
-                const double eff = (double)items / ((double)waves * (double)g);
-                if (eff > best + 1e-9) { best = eff; blocks = g; }
-            }
-        }
         blocks = std::min<uint64_t>(blocks, kMaxGridBlocks);
         const double dt = p->T / (double)(N - 1);
         CB_CUDA(launch_heston_conditional(k, (float)p->sigma_v, (float)p->rho, (float)dt, threads, (int)blocks, ws,

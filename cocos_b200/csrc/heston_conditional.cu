@@ -49,7 +49,7 @@ __device__ __forceinline__ float cond_angle(uint32_t lo, uint32_t hi, uint32_t o
     return __uint_as_float(r);
 }
 
-template <bool MULTI>
+template <bool MULTI, bool XCHG>
 __global__ void __launch_bounds__(kFusedMaxThreads)
 heston_conditional_kernel(const __grid_constant__ FusedConsts<float> c, ReduceWorkspace ws, float sigma_v, float rho,
                           float dt, float *__restrict__ x_out, float *__restrict__ v_out) {
@@ -81,6 +81,7 @@ heston_conditional_kernel(const __grid_constant__ FusedConsts<float> c, ReduceWo
         const bool active = local < c.pair_count;
         const uint64_t gp = c.pair_first + (active ? local : 0);
         const bool paired = active && gp < c.partnered;
+        if (!__any_sync(0xffffffffu, active)) continue;      // last round: this warp lies wholly past the end of the shard
         PairStream rng;
         rng.init((uint32_t)gp, (uint32_t)(gp >> 32), c.subsequence, c.keys);
         CondState s{c.v0, c.v0, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -138,18 +139,24 @@ heston_conditional_kernel(const __grid_constant__ FusedConsts<float> c, ReduceWo
         acc.add(mufu_ex2(xT1 * 1.4426950408889634f), mufu_ex2(xT2 * 1.4426950408889634f), active, paired, c.strikes[0],
                 s_strikes, lane);
     }
-    acc.publish(c.nK, ws);
+    acc.template publish<XCHG>(c.nK, ws);
 }
 
 cudaError_t launch_heston_conditional(const FusedConsts<float> &c, float sigma_v, float rho, float dt, int threads,
                                       int blocks, ReduceWorkspace ws, float *d_x, float *d_v, cudaStream_t stream) {
-    if (c.nK > 1) heston_conditional_kernel<true><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);
-    else heston_conditional_kernel<false><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);
+    const bool x = ws.px.nranks > 1;
+    if (c.nK > 1) {
+        if (x) heston_conditional_kernel<true, true><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);
+        else heston_conditional_kernel<true, false><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);
+    } else {
+        if (x) heston_conditional_kernel<false, true><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);
+        else heston_conditional_kernel<false, false><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t conditional_occupancy(int threads, bool multi, int *blocks_per_sm) {
-    const void *fn = multi ? (const void *)heston_conditional_kernel<true> : (const void *)heston_conditional_kernel<false>;
+    const void *fn = multi ? (const void *)heston_conditional_kernel<true, false> : (const void *)heston_conditional_kernel<false, false>;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
 }
 

@@ -128,7 +128,8 @@ __device__ __forceinline__ void euler_pair(real &x1, real &u1, real &x2, real &u
 // ---- the kernel -------------------------------------------------------------
 
 // PAYOFF: 0 terminal (European), 1 arithmetic-average Asian, 2 knock-out barrier -- path functionals in registers
-template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1, int ROUNDS = 10, int PAYOFF = 0>
+template <typename real, int PPT, bool MULTI, bool TRAJ, bool PIPE = true, int MINB = 1, int ROUNDS = 10, int PAYOFF = 0,
+          bool XCHG = false>
 __global__ void __launch_bounds__(kMaxThreads, MINB)
 heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace ws,
                     real *__restrict__ x_out, real *__restrict__ v_out, real *__restrict__ traj) {
@@ -165,6 +166,9 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             x1[q] = x2[q] = (real)0;
             v1[q] = v2[q] = k.u0;            // v1/v2 hold u = c1*v inside the time loop
         }
+        // last grid-stride round only: a warp that lies wholly past the end of the shard leaves its issue slots to the
+        // warps that still have pairs (local[0] is the smallest index of the thread)
+        if (!__any_sync(0xffffffffu, active[0])) continue;
         // trajectory mode: this thread's slots in the current row [first halves | partners]; a warp writes 128
         // contiguous bytes per half and step (predicated at the ragged edge), rows advance by row_len per step
         real *row1[PPT], *row2[PPT];
@@ -285,7 +289,7 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
             acc.add(S1, S2, active[q], paired[q], c.strikes[0], s_strikes, lane, c.payoff_sign);
         }
     }
-    acc.publish(c.nK, ws);
+    acc.template publish<XCHG>(c.nK, ws);
 }
 
 // ---- host side ---------------------------------------------------------------
@@ -325,6 +329,17 @@ static const void *variant_fn(int ppt, int variant) {
     return ppt == 1 ? variant_fn<1>(variant) : ppt == 2 ? variant_fn<2>(variant) : variant_fn<4>(variant);
 }
 
+// pairs per thread of the kernels instantiated with the fused cross-GPU exchange = the host's default per type
+template <typename real>
+constexpr int kExchangePairs = sizeof(real) == 8 ? 2 : 1;
+
+template <typename real>
+bool fused_exchange_supported(const LaunchShape &s, int payoff_kind, bool traj) {
+    return payoff_kind == 0 && !traj && s.variant == 0 && s.pairs_per_thread == kExchangePairs<real>;
+}
+template bool fused_exchange_supported<float>(const LaunchShape &, int, bool);
+template bool fused_exchange_supported<double>(const LaunchShape &, int, bool);
+
 template <typename real>
 cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s, ReduceWorkspace ws,
                                 real *d_x, real *d_v, real *d_traj, cudaStream_t stream) {
@@ -337,6 +352,17 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
                      : (const void *)heston_fused_kernel<real, 1, false, false, true, 1, 10, 1>)
             : (multi ? (const void *)heston_fused_kernel<real, 1, true, false, true, 1, 10, 2>
                      : (const void *)heston_fused_kernel<real, 1, false, false, true, 1, 10, 2>);
+        return cudaLaunchKernel(fn, dim3(s.blocks), dim3(s.threads), args, 0, stream);
+    }
+    if (ws.px.nranks > 1) {
+        // the instantiations that carry the fused cross-GPU step: the default geometry of each type (capi.cu asks
+        // fused_exchange_supported first and keeps the NCCL allreduce for everything else)
+        if (!fused_exchange_supported<real>(s, c.payoff_kind, d_traj != nullptr)) return cudaErrorInvalidValue;
+        void *args[] = {(void *)&c, (void *)&ws, (void *)&d_x, (void *)&d_v, (void *)&d_traj};
+        constexpr int P = kExchangePairs<real>;
+        const void *fn = multi
+            ? (const void *)heston_fused_kernel<real, P, true, false, true, (P == 1 ? kSweepMinBlocks<real> : 1), 10, 0, true>
+            : (const void *)heston_fused_kernel<real, P, false, false, true, (P == 2 ? kTwoPairMinBlocks<real> : 1), 10, 0, true>;
         return cudaLaunchKernel(fn, dim3(s.blocks), dim3(s.threads), args, 0, stream);
     }
     if (d_traj != nullptr)

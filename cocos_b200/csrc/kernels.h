@@ -76,6 +76,10 @@ template <typename real>
 cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &shape, ReduceWorkspace ws,
                                 real *d_x, real *d_v, real *d_traj, cudaStream_t stream);
 
+// true when launch_heston_fused has an instantiation with the fused cross-GPU exchange for this launch
+template <typename real>
+bool fused_exchange_supported(const LaunchShape &shape, int payoff_kind, bool traj);
+
 template <typename real>
 cudaError_t fused_occupancy(int threads, int pairs_per_thread, bool multi, int variant, int *blocks_per_sm, int *regs);
 
