@@ -69,7 +69,8 @@ struct cb_comm {
     int dev = -1;
     void *xchg = nullptr;                 // owned: kExchangeBytes on `dev`
     void *imported[kMaxPeers] = {};       // cudaIpcOpenMemHandle mappings (other processes' buffers)
-    PeerExchange px = {};
+    PeerExchange px = {};                 // host copy of the mapping table
+    PeerExchange *d_px = nullptr;         // the same on `dev` (what the kernels read)
     bool p2p = false;
     unsigned int epoch = 0;
 };
@@ -368,12 +369,22 @@ static int exchange_allocate(cb_comm *m, int dev) {
     return CB_OK;
 }
 
+// copies the finished mapping table to the device; the kernels read it from there
+static int exchange_publish_table(cb_comm *m) {
+    CB_CUDA(cudaSetDevice(m->dev));
+    if (m->d_px == nullptr) CB_CUDA(cudaMalloc(&m->d_px, sizeof(PeerExchange)));
+    CB_CUDA(cudaMemcpy(m->d_px, &m->px, sizeof(PeerExchange), cudaMemcpyHostToDevice));
+    return CB_OK;
+}
+
 static void exchange_release(cb_comm *m) {
     if (m->dev >= 0) cudaSetDevice(m->dev);
     for (int p = 0; p < kMaxPeers; ++p)
         if (m->imported[p]) cudaIpcCloseMemHandle(m->imported[p]);
     if (m->xchg) cudaFree(m->xchg);
+    if (m->d_px) cudaFree(m->d_px);
     m->xchg = nullptr;
+    m->d_px = nullptr;
     m->p2p = false;
 }
 
@@ -400,8 +411,9 @@ static bool exchange_connect_local(int n, cb_ctx *const *ctxs, cb_comm **comms) 
         if (exchange_allocate(comms[i], ctxs[i]->dev) != CB_OK) return false;
     for (int i = 0; i < n; ++i) {
         for (int p = 0; p < n; ++p) exchange_point(comms[i], p, comms[p]->xchg);
-        comms[i]->p2p = true;
+        if (exchange_publish_table(comms[i]) != CB_OK) return false;
     }
+    for (int i = 0; i < n; ++i) comms[i]->p2p = true;
     return true;
 }
 
@@ -442,6 +454,8 @@ extern "C" CB_API int cb_comm_p2p_enable(cb_comm *m, int enable) {
     if (enable) {
         CB_REQUIRE(m->xchg != nullptr, "no exchange buffer: export/import first");
         for (int p = 0; p < m->nranks; ++p) CB_REQUIRE(m->px.slots[p] != nullptr, "rank %d is not mapped", p);
+        int rc = exchange_publish_table(m);
+        if (rc) return rc;
     }
     m->p2p = enable != 0;
     return CB_OK;
@@ -786,8 +800,8 @@ extern "C" CB_API int cb_heston_terminal_injected_host_f32(cb_ctx *c, const floa
 // hands the kernel this launch's view of the communicator's peer mappings; false = no fused exchange
 static bool exchange_arm(cb_comm *comm, ReduceWorkspace *ws) {
     if (comm == nullptr || !comm->p2p) return false;
-    ws->px = comm->px;
-    ws->px.epoch = ++comm->epoch;
+    ws->px = comm->d_px;
+    ws->epoch = ++comm->epoch;
     return true;
 }
 

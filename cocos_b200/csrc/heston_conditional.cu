@@ -144,7 +144,7 @@ heston_conditional_kernel(const __grid_constant__ FusedConsts<float> c, ReduceWo
 
 cudaError_t launch_heston_conditional(const FusedConsts<float> &c, float sigma_v, float rho, float dt, int threads,
                                       int blocks, ReduceWorkspace ws, float *d_x, float *d_v, cudaStream_t stream) {
-    const bool x = ws.px.nranks > 1;
+    const bool x = ws.px != nullptr;
     if (c.nK > 1) {
         if (x) heston_conditional_kernel<true, true><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);
         else heston_conditional_kernel<true, false><<<blocks, threads, 0, stream>>>(c, ws, sigma_v, rho, dt, d_x, d_v);

@@ -354,7 +354,7 @@ cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &s
                      : (const void *)heston_fused_kernel<real, 1, false, false, true, 1, 10, 2>);
         return cudaLaunchKernel(fn, dim3(s.blocks), dim3(s.threads), args, 0, stream);
     }
-    if (ws.px.nranks > 1) {
+    if (ws.px != nullptr) {
         // the instantiations that carry the fused cross-GPU step: the default geometry of each type (capi.cu asks
         // fused_exchange_supported first and keeps the NCCL allreduce for everything else)
         if (!fused_exchange_supported<real>(s, c.payoff_kind, d_traj != nullptr)) return cudaErrorInvalidValue;

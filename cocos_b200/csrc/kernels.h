@@ -56,7 +56,6 @@ constexpr int kMaxPeers = 8;
 struct PeerExchange {
     int nranks;                       // < 2: no exchange
     int rank;
-    unsigned int epoch;               // launch number on this communicator (> 0), identical on every rank
     double *slots[kMaxPeers];         // rank p's buffer, mapped here: [2][kMaxPeers][kMaxAcc]
     unsigned int *flags[kMaxPeers];   // rank p's flags, mapped here: [kMaxPeers], flags[r] = last epoch published by r
 };
@@ -69,7 +68,10 @@ struct ReduceWorkspace {
     double *partials;    // [kMaxGridBlocks][kMaxAcc]
     unsigned int *ticket;
     double *result;      // [kMaxAcc]: sums[nK] then sumsq[nK]
-    PeerExchange px;
+    // fused cross-GPU step (XCHG kernels only): the communicator's mapping table, resident on this device -- eight bytes
+    // of kernel parameters instead of the table itself, read by the last block only -- and this launch's number
+    const PeerExchange *px;
+    unsigned int epoch;  // launch number on the communicator (> 0), identical on every rank
 };
 
 template <typename real>

@@ -136,17 +136,18 @@ struct PayoffAccumulator {
         }
         if (threadIdx.x == 0) *ws.ticket = 0u;   // ready for the next launch on this stream
         if constexpr (XCHG) {
-            if (ws.px.nranks > 1) exchange(nacc, ws);
+            if (ws.px != nullptr) exchange(nacc, ws.result, ws.px, ws.epoch);
         }
     }
 
     // The fused cross-GPU step (see PeerExchange); runs in the last block only, after ws.result holds this rank's totals.
-    static __device__ __forceinline__ void exchange(int nacc, const ReduceWorkspace &ws) {
-        const PeerExchange &px = ws.px;
-        const size_t parity_base = (size_t)(px.epoch & 1u) * kMaxPeers * kMaxAcc;
+    // (a real call, not inlined: the time loop of the kernel keeps the schedule it has without this code)
+    static __device__ __noinline__ void exchange(int nacc, double *result, const PeerExchange *table, unsigned int epoch) {
+        const PeerExchange &px = *table;
+        const size_t parity_base = (size_t)(epoch & 1u) * kMaxPeers * kMaxAcc;
         __syncthreads();                                        // result[] was written by threads of this block
         for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
-            const double t = ws.result[a];
+            const double t = result[a];
             for (int p = 0; p < px.nranks; ++p) px.slots[p][parity_base + (size_t)px.rank * kMaxAcc + a] = t;
         }
         __threadfence_system();                                 // the slots are out before any flag is
@@ -156,13 +157,13 @@ struct PayoffAccumulator {
         __syncthreads();
         if ((int)threadIdx.x < px.nranks) {
             unsigned int *remote = px.flags[threadIdx.x] + px.rank;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(px.epoch) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
             const unsigned int *mine = px.flags[px.rank] + threadIdx.x;
             const long long t0 = clock64();
             for (;;) {
                 unsigned int seen;
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-                if ((int)(seen - px.epoch) >= 0) break;
+                if ((int)(seen - epoch) >= 0) break;
                 if (clock64() - t0 > 20000000000ll) { s_timed_out = 1; break; }   // ~10 s: a rank never launched
                 __nanosleep(64);
             }
@@ -173,7 +174,7 @@ struct PayoffAccumulator {
             double t = 0.0;
             for (int r = 0; r < px.nranks; ++r)
                 t += __ldcg(px.slots[px.rank] + parity_base + (size_t)r * kMaxAcc + a);
-            ws.result[a] = dead ? __longlong_as_double((long long)kExchangeTimeoutBits) : t;
+            result[a] = dead ? __longlong_as_double((long long)kExchangeTimeoutBits) : t;
         }
     }
 };
