@@ -43,7 +43,7 @@ typedef enum {
 } cb_status;
 
 typedef struct cb_ctx cb_ctx;       /* one device + one stream + workspace */
-typedef struct cb_comm cb_comm;     /* one NCCL communicator rank */
+typedef struct cb_comm cb_comm;     /* one rank of a communicator: NCCL handle + NVLink peer mappings */
 
 /* Heston model scalars: the arguments of simulate_heston_model
  * (examples/stochastic_volatility/heston_utilities.py:24-35). */
@@ -162,10 +162,13 @@ CB_API int cb_heston_terminal_injected_host_f32(cb_ctx *ctx, const float *h_Z, c
  *                 pair p owns paths p and p+ceil(R/2); the last pair of an odd R
  *                 has no partner
  *   h_strikes[nK] strikes sharing the same paths (1 <= nK <= CB_MAX_STRIKES)
- *   comm          NULL, or a communicator: one ncclAllReduce(sum, double) of the
- *                 2*nK partial sums follows the kernel on the same stream
- *                 (replaces ComputeDevicePool.map_reduce's host fold,
- *                 cocos/multi_processing/device_pool.py:246-251)
+ *   comm          NULL, or a communicator: the 2*nK partial sums of all ranks are
+ *                 added up (replaces ComputeDevicePool.map_reduce's host fold,
+ *                 cocos/multi_processing/device_pool.py:246-251) -- inside the
+ *                 kernel over NVLink peer memory when the communicator has peer
+ *                 mappings (cb_comm_p2p_*) and the launch uses the default
+ *                 geometry, else by one ncclAllReduce(sum, double) behind the
+ *                 kernel on the same stream; every rank must make the same call
  *   d_x, d_v      NULL, or device arrays receiving terminal values of this shard:
  *                 path of pair p at [p-pair_first], partner at
  *                 [pair_count + p-pair_first] (reference layout when the shard is
