@@ -1,5 +1,6 @@
 """Host-side mirror of the reference interface: pure-Python pieces, no GPU needed."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -134,3 +135,19 @@ def test_bundle_protocol():
     assert select_num_pack(True) is cn
     with pytest.raises(NotImplementedError):
         select_num_pack(False)
+
+
+def test_bundled_nccl_is_found_without_importing_torch():
+    """The ctypes layer names torch's own libnccl to the C library before any communicator exists (a later
+    `import torch` must not find an older system copy resident under the same SONAME)."""
+    import subprocess
+    import sys
+    code = ("import sys, os\n"
+            "from cocos_b200 import _lib\n"
+            "p = _lib._bundled_nccl()\n"
+            "assert 'torch' not in sys.modules\n"
+            "assert p is None or (os.path.isabs(p) and os.path.exists(p) and p.endswith('libnccl.so.2')), p\n"
+            "print('ok', p)\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stderr[-1500:]
