@@ -215,7 +215,7 @@ extern "C" CB_API int cb_ctx_set_launch(cb_ctx *c, int threads, int blocks_per_s
 
 extern "C" CB_API int cb_ctx_set_variant(cb_ctx *c, int variant) {
     CB_REQUIRE(c != nullptr, "context is NULL");
-    CB_REQUIRE(variant >= 0 && variant <= 3, "variant must be in [0,3]");
+    CB_REQUIRE(variant >= 0 && variant <= 2, "variant must be in [0,2]");
     c->variant = variant;
     return CB_OK;
 }

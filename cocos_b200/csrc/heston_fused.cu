@@ -315,13 +315,13 @@ static cudaError_t launch_one(const FusedConsts<real> &c, const LaunchShape &s, 
     return cudaGetLastError();
 }
 
-// experimental variants of the float single-strike kernel (variant = 1..3), selected by cb_ctx_set_variant
+// tuning variants of the float single-strike kernel (variant = 1, 2), selected by cb_ctx_set_variant; all run the
+// full Philox4x32-10
 template <int PPT>
 static const void *variant_fn(int variant) {
     switch (variant) {
         case 1: return (const void *)heston_fused_kernel<float, PPT, false, false, false, 1>;          // not software-pipelined
         case 2: return (const void *)heston_fused_kernel<float, PPT, false, false, true, (PPT == 4 ? 2 : 4)>;
-        case 3: return (const void *)heston_fused_kernel<float, PPT, false, false, true, 1, 6>;   // timing experiment only: 6 Philox rounds
         default: return (const void *)heston_fused_kernel<float, PPT, false, false, true, 1>;
     }
 }

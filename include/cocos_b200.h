@@ -80,7 +80,8 @@ CB_API int cb_timer_start(cb_ctx *ctx);
 CB_API int cb_timer_stop(cb_ctx *ctx, float *elapsed_ms);             /* synchronises the stop event */
 /* tuning knobs of the fused kernels: threads per block, blocks per SM, pairs per thread (0 = default) */
 CB_API int cb_ctx_set_launch(cb_ctx *ctx, int threads, int blocks_per_sm, int pairs_per_thread);
-/* kernel-variant selector used while tuning (0 = default) */
+/* kernel-variant selector used while tuning (0 = default, 1 = no software pipelining, 2 = register-capped); every
+ * variant computes the same stream and the same results */
 CB_API int cb_ctx_set_variant(cb_ctx *ctx, int variant);
 
 /* caller-side memory helpers for hosts that do not bring their own allocator */

@@ -54,7 +54,7 @@ def main():
               f"{rate:.3e} path-steps/s  mean payoff {mean:.5f}", flush=True)
 
     if mode == "variants":
-        for variant in (0, 1, 2, 3):
+        for variant in (0, 1, 2):
             for threads in (128, 256):
                 for ppt in (1, 2, 4):
                     for bps in (0, 8, 12, 16, 32, 64):
