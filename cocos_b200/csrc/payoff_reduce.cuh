@@ -164,7 +164,7 @@ struct PayoffAccumulator {
                 unsigned int seen;
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
                 if ((int)(seen - epoch) >= 0) break;
-                if (clock64() - t0 > 20000000000ll) { s_timed_out = 1; break; }   // ~10 s: a rank never launched
+                if (clock64() - t0 > 120000000000ll) { s_timed_out = 1; break; }  // ~60 s: a rank never launched
                 __nanosleep(64);
             }
         }
