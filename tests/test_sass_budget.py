@@ -1,0 +1,75 @@
+"""Instruction budget of the fused kernels' time loops, read from the SASS of the built library (no GPU needed).
+
+The headline kernel is bound by the issue port (cycles per pair-step = instructions + 3 per
+IMAD.WIDE), so its speed is its instruction count: this pins the count, the Philox multiplies, the MUFU count and the
+absence of instructions that share the XU pipe with MUFU (I2F/F2F) or touch memory inside the loop.
+"""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+SO = os.path.join(ROOT, "cocos_b200", "libcocos_b200.so")
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump is not on PATH")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    return subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
+
+
+def _loop(sass, prefix):
+    """Opcodes of the shortest backward-branch loop that contains MUFU in the first kernel whose name starts with prefix."""
+    for f in re.split(r"\n\s*Function : ", sass)[1:]:
+        if not f.startswith(prefix):
+            continue
+        lines = []
+        for l in f.splitlines():
+            m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", l)
+            if m:
+                lines.append((int(m.group(1), 16), m.group(2).strip()))
+        best = None
+        for i, (addr, ins) in enumerate(lines):
+            m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", ins)
+            if m and int(m.group(1), 16) < addr:
+                j = next(k for k, (a, _) in enumerate(lines) if a == int(m.group(1), 16))
+                body = [re.sub(r"^@!?U?P\d\s+", "", x).split()[0] for _, x in lines[j:i + 1]]
+                if any(o.startswith("MUFU") for o in body) and (best is None or len(body) < len(best)):
+                    best = body
+        return best
+    raise AssertionError(f"no kernel {prefix} in the library")
+
+
+HEADLINE = "_ZN2cb19heston_fused_kernelIfLi1ELb0ELb0ELb1ELi1ELi10ELi0ELb0E"
+HEADLINE_XCHG = "_ZN2cb19heston_fused_kernelIfLi1ELb0ELb0ELb1ELi1ELi10ELi0ELb1E"
+
+
+def test_headline_loop_budget(sass):
+    ops = _loop(sass, HEADLINE)                       # one trip = 2 Philox blocks = 6 Euler steps of an antithetic pair
+    wide = sum(o.startswith("IMAD.WIDE") for o in ops)
+    mufu = sum(o.startswith("MUFU") for o in ops)
+    assert mufu == 30                                 # 5 per pair-step: lg2, sin, cos, 2 x sqrt
+    assert wide == 34                                 # 17 per Philox4x32-10 block (rounds 0-1 hoisted)
+    assert len(ops) <= 240                            # 238 when written: 56.7 issue cycles per pair-step
+    for bad in ("I2F", "F2F", "I2FP", "LDG", "STG", "LDL", "STL", "LDS", "STS", "LDC"):
+        assert not any(o.startswith(bad) for o in ops), bad
+    cycles_per_pair_step = (len(ops) + 3 * wide) / 6.0
+    assert cycles_per_pair_step < 57.5
+
+
+def test_exchange_instantiation_keeps_the_schedule(sass):
+    """The kernel with the fused cross-GPU exchange has the same time loop, opcode by opcode."""
+    assert _loop(sass, HEADLINE) == _loop(sass, HEADLINE_XCHG)
+
+
+def test_f64_and_conditional_loop_budgets(sass):
+    f64 = _loop(sass, "_ZN2cb19heston_fused_kernelIdLi2ELb0ELb0ELb1ELi2ELi10ELi0ELb0E")     # 2 pairs x 6 steps per trip
+    n64 = sum(o.split(".")[0] in ("DFMA", "DMUL", "DADD", "DSETP") for o in f64)
+    assert sum(o.startswith("MUFU") for o in f64) == 60 and n64 <= 240 and len(f64) <= 690   # 20 FP64 per pair-step
+    cond = _loop(sass, "_ZN2cb25heston_conditional_kernelILb0ELb0E")                           # 6 steps per trip
+    assert sum(o.startswith("MUFU") for o in cond) == 24                                       # 4 per pair-step
+    assert sum(o.startswith("IMAD.WIDE") for o in cond) == 17 and len(cond) <= 172
