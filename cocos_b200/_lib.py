@@ -101,6 +101,7 @@ PROTOTYPES = {
     "cb_comm_p2p_import": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cb_comm_p2p_enable": (c_int, [c_void_p, c_int]),
     "cb_comm_p2p_active": (c_int, [c_void_p, P(c_int)]),
+    "cb_comm_p2p_disconnect": (c_int, [c_void_p]),
     "cb_allreduce_sum_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_size]),
     "cb_group_start": (c_int, []),
     "cb_group_end": (c_int, []),

@@ -461,6 +461,22 @@ extern "C" CB_API int cb_comm_p2p_enable(cb_comm *m, int enable) {
     return CB_OK;
 }
 
+// Unmaps the other processes' buffers and turns the fused exchange off.  An exported buffer must not be freed while
+// another process still has it mapped: every rank disconnects, the host synchronises the ranks, then cb_comm_destroy.
+extern "C" CB_API int cb_comm_p2p_disconnect(cb_comm *m) {
+    CB_REQUIRE(m != nullptr, "comm is NULL");
+    m->p2p = false;
+    if (m->dev >= 0) CB_CUDA(cudaSetDevice(m->dev));
+    for (int p = 0; p < kMaxPeers; ++p)
+        if (m->imported[p]) {
+            cudaIpcCloseMemHandle(m->imported[p]);
+            m->imported[p] = nullptr;
+            m->px.slots[p] = nullptr;
+            m->px.flags[p] = nullptr;
+        }
+    return CB_OK;
+}
+
 extern "C" CB_API int cb_comm_p2p_active(const cb_comm *m, int *active) {
     CB_REQUIRE(m != nullptr && active != nullptr, "NULL argument");
     *active = m->p2p ? 1 : 0;

@@ -116,5 +116,15 @@ class ShardedPricer:
 
     def close(self):
         if self.comm is not None:
+            if self.peer_exchange:
+                # two phases: nobody frees its exported buffer while another rank still has it mapped
+                _lib.lib().cb_comm_p2p_disconnect(self.comm)
+                self.peer_exchange = False
+                try:
+                    import torch.distributed as dist
+                    if dist.is_available() and dist.is_initialized():
+                        dist.barrier()
+                except Exception:       # noqa: BLE001  (the process group may already be gone at interpreter exit)
+                    pass
             _lib.lib().cb_comm_destroy(self.comm)
             self.comm = None

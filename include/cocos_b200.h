@@ -252,6 +252,9 @@ CB_API int cb_comm_p2p_export(cb_ctx *ctx, cb_comm *comm, void *h_handle /* CB_P
 CB_API int cb_comm_p2p_import(cb_ctx *ctx, cb_comm *comm, const void *h_handles /* nranks * CB_P2P_HANDLE_BYTES */);
 CB_API int cb_comm_p2p_enable(cb_comm *comm, int enable);
 CB_API int cb_comm_p2p_active(const cb_comm *comm, int *active);
+/* Tear-down across processes: every rank unmaps its peers' buffers, the host synchronises the ranks, then each
+ * rank calls cb_comm_destroy (an exported buffer must not be freed while another process still maps it). */
+CB_API int cb_comm_p2p_disconnect(cb_comm *comm);
 CB_API int cb_allreduce_sum_f64(cb_ctx *ctx, cb_comm *comm, double *d_buf, size_t count);
 CB_API int cb_group_start(void);
 CB_API int cb_group_end(void);
