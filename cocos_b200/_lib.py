@@ -76,6 +76,10 @@ PROTOTYPES = {
                                            c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_heston_price_launch_f64": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,
                                            c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb_heston_trajectory_launch_f32": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,
+                                                c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cb_heston_trajectory_launch_f64": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,
+                                                c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cb_heston_price_conditional_launch_f32": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64,
                                                        c_u32, c_u64, c_u64, c_void_p, c_void_p, c_void_p]),
     "cb_heston_payoff_launch_f32": (c_int, [c_void_p, P(HestonParams), c_u64, c_u32, P(c_double), c_int, c_u64, c_u32,

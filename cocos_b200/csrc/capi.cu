@@ -59,6 +59,7 @@ struct cb_ctx {
     size_t scratch_bytes = 0;
     int threads = 0, blocks_per_sm = 0, ppt = 0;   // 0 = default
     int variant = 0;
+    int pi_blocks_per_sm[2] = {0, 0};        // occupancy of pi_count_kernel<plain / antithetic>
     std::map<std::tuple<int, int, int, int, int>, std::pair<int, int>> occ_cache;   // (is64, ppt, multi, threads, variant) -> (bps, regs)
 };
 
@@ -279,6 +280,7 @@ NcclApi g_nccl;
 std::once_flag g_nccl_once;
 
 std::string g_nccl_path;   // cb_nccl_library(); else $COCOS_B200_NCCL_LIBRARY
+std::string g_nccl_why;    // why loading failed: the dlerror() text, captured right where it happened
 
 void load_nccl() {
     // 1. a libnccl already mapped into the process (the host framework's copy);
@@ -299,11 +301,17 @@ void load_nccl() {
         for (const char *nm : names) {
             g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
             if (g_nccl.handle) break;
+            const char *why = dlerror();                    // reading it clears it: read once, keep the text
+            g_nccl_why = why ? why : "dlopen failed";
         }
     if (!g_nccl.handle) return;
-#define CB_SYM(field, name) \
-    *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, name); \
-    if (!g_nccl.field) return;
+#define CB_SYM(field, name)                                         \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, name);         \
+    if (!g_nccl.field) {                                            \
+        const char *why = dlerror();                                \
+        g_nccl_why = why ? why : std::string("missing symbol ") + name; \
+        return;                                                     \
+    }
     CB_SYM(GetUniqueId, "ncclGetUniqueId")
     CB_SYM(CommInitRank, "ncclCommInitRank")
     CB_SYM(CommInitAll, "ncclCommInitAll")
@@ -318,7 +326,7 @@ void load_nccl() {
 
 int need_nccl() {
     std::call_once(g_nccl_once, load_nccl);
-    if (!g_nccl.ok) return fail(CB_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "missing symbol");
+    if (!g_nccl.ok) return fail(CB_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", g_nccl_why.c_str());
     return CB_OK;
 }
 }  // namespace
@@ -353,7 +361,7 @@ extern "C" CB_API int cb_comm_unique_id(void *h_id) {
 // ---- fused peer exchange: set-up ------------------------------------------------------------------------------
 
 static void exchange_point(cb_comm *m, int peer, void *base) {
-    m->px.slots[peer] = reinterpret_cast<double *>(base);
+    m->px.slots[peer] = reinterpret_cast<unsigned long long *>(base);
     m->px.flags[peer] = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(base) + kExchangeSlotBytes);
 }
 
@@ -813,12 +821,38 @@ extern "C" CB_API int cb_heston_terminal_injected_host_f32(cb_ctx *c, const floa
 
 // ---------------------------------------------------------------- Heston: fused kernel
 
-// hands the kernel this launch's view of the communicator's peer mappings; false = no fused exchange
-static bool exchange_arm(cb_comm *comm, ReduceWorkspace *ws) {
+// Hands the kernel this launch's view of the communicator's peer mappings; false = no fused exchange.
+// The launch number is only COMMITTED (exchange_commit) once the launch has been accepted by the runtime: a launch
+// that fails leaves the communicator where it was, so the ranks' counters cannot drift apart on an error path.
+// `sig` identifies the call (what is launched, on which seed/subsequence and sizes); every rank must pass the same
+// one, the slots' tags carry it and a rank that folds another call's data gets the poison value instead of a sum.
+static bool exchange_arm(cb_comm *comm, ReduceWorkspace *ws, unsigned int sig) {
     if (comm == nullptr || !comm->p2p) return false;
     ws->px = comm->d_px;
-    ws->epoch = ++comm->epoch;
+    ws->epoch = comm->epoch + 1;
+    ws->sig = sig;
     return true;
+}
+static void exchange_commit(cb_comm *comm) { ++comm->epoch; }
+
+static unsigned int call_signature(unsigned int kind, uint64_t seed, uint32_t subsequence, uint64_t a, uint64_t b) {
+    uint64_t h = 0x9E3779B97F4A7C15ull * (kind + 1);
+    for (uint64_t v : {seed, (uint64_t)subsequence, a, b}) {
+        h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 31;
+    }
+    return (unsigned int)(h & 0xFFFFFFu);
+}
+
+// `result` after a fused exchange: the poison values say what went wrong
+static int check_exchange_poison(unsigned long long first_bits) {
+    if (first_bits == kExchangeTimeoutBits)
+        return fail(CB_ERR_CUDA, "fused peer exchange timed out: a rank of the communicator never launched its shard");
+    if (first_bits == kExchangeMismatchBits)
+        return fail(CB_ERR_CUDA, "fused peer exchange: a rank published another launch's data (the ranks' launch "
+                                 "sequences differ: every rank must issue the same calls in the same order)");
+    return CB_OK;
 }
 
 template <typename real>
@@ -854,17 +888,24 @@ static FusedConsts<real> make_consts(const cb_heston_params *p, uint64_t R, uint
 // Geometry: a grid of (resident blocks per SM) x (SM count) blocks, grid-stride over the shard's pairs.  The last
 // round is usually partial: warps that lie wholly past the end skip it (heston_fused_kernel), so its cost is
 // proportional to what is left and the largest residency is always the best choice.
+// `xchg`: the launch goes through a communicator with NVLink peer mappings.  Every rank must then run the SAME
+// instantiation, so the per-context tuning overrides (pairs per thread, variant) are ignored and the default
+// geometry of the type -- the one the exchange kernels are built for -- is used; eligibility for the fused
+// exchange is thereby a property of the communicator, not of a context.
 template <typename real>
-static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, LaunchShape *s) {
+static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, int payoff_kind, bool xchg, LaunchShape *s) {
     // defaults from the tools/tune_fused.py sweeps: float 256 threads x 1 pair, double 128 threads x 2 pairs
+    const int default_ppt = sizeof(real) == 8 ? 2 : 1;
     const int threads = c->threads ? c->threads : (sizeof(real) == 8 ? 128 : 256);
-    const int ppt = traj ? 1 : (c->ppt ? c->ppt : (sizeof(real) == 8 ? 2 : 1));
-    const int variant = (sizeof(real) == 4 && !multi && !traj) ? c->variant : 0;
-    const auto key = std::make_tuple((int)(sizeof(real) == 8), traj ? -1 : ppt, (int)multi, threads, variant);
+    const int ppt = payoff_kind != 0 ? 1 : (xchg || !c->ppt) ? default_ppt : c->ppt;
+    const int variant = (sizeof(real) == 4 && !multi && payoff_kind == 0 && !xchg) ? c->variant : 0;
+    const bool with_exchange = xchg && payoff_kind == 0;      // the path-dependent kernels carry the exchange anyway
+    const auto key = std::make_tuple((int)(sizeof(real) == 8), ppt, (int)multi, threads,
+                                     variant + 16 * payoff_kind + 64 * (int)with_exchange);
     auto it = c->occ_cache.find(key);
     if (it == c->occ_cache.end()) {
         int bps = 0, regs = 0;
-        CB_CUDA((fused_occupancy<real>(threads, traj ? -1 : ppt, multi, variant, &bps, &regs)));
+        CB_CUDA((fused_occupancy<real>(threads, ppt, multi, payoff_kind, variant, with_exchange, &bps, &regs)));
         it = c->occ_cache.emplace(key, std::make_pair(bps, regs)).first;
     }
     int bps = it->second.first;
@@ -890,7 +931,8 @@ static int choose_shape(cb_ctx *c, uint64_t pair_count, bool multi, bool traj, L
 template <typename real>
 static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N, const double *h_strikes,
                                int nK, uint64_t seed, uint32_t subsequence, uint64_t pair_first, uint64_t pair_count,
-                               cb_comm *comm, real *d_x, real *d_v, real *d_traj, const cb_payoff_spec *spec = nullptr) {
+                               cb_comm *comm, real *d_x, real *d_v, real *d_traj, real *d_traj_v,
+                               const cb_payoff_spec *spec = nullptr) {
     CB_CTX(c);
     int rc = check_heston(p, R, N);
     if (rc) return rc;
@@ -900,7 +942,9 @@ static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R,
     CB_REQUIRE(pair_first <= H && pair_count <= H - pair_first, "pair range [%llu,+%llu) outside [0,%llu)",
                (unsigned long long)pair_first, (unsigned long long)pair_count, (unsigned long long)H);
     CB_REQUIRE((d_x == nullptr) == (d_v == nullptr), "d_x and d_v must both be given or both be NULL");
-    if (comm != nullptr) {
+    CB_REQUIRE(d_traj_v == nullptr || d_traj != nullptr, "the variance trajectory comes with the log-price trajectory");
+    const bool p2p = comm != nullptr && comm->p2p;
+    if (comm != nullptr && !p2p) {
         rc = need_nccl();
         if (rc) return rc;
     }
@@ -917,22 +961,34 @@ static int heston_price_launch(cb_ctx *c, const cb_heston_params *p, uint64_t R,
             k.barrier_log = (real)(sgn * std::log(spec->barrier));
         }
     }
-    // the cross-GPU sum: fused into the kernel's last block over NVLink peer mappings when the communicator has
-    // them (an empty shard still launches one block to publish its zeros), else one ncclAllReduce behind the kernel
-    // (kernels with the exchange exist for the default geometry of plain pricing launches; the rest keep NCCL)
+    // The cross-GPU sum is fused into the kernel's last block over NVLink peer mappings whenever the communicator
+    // has them -- every launch type carries it (an empty shard still launches one block to publish its zeros);
+    // a communicator without peer mappings gets one ncclAllReduce behind the kernel instead.
     ReduceWorkspace ws = c->ws;
-    LaunchShape shape;
-    rc = choose_shape<real>(c, pair_count, nK > 1, d_traj != nullptr, &shape);
-    if (rc) return rc;
-    if (k.payoff_kind != 0 || k.payoff_sign < (real)0) shape.variant = 0;
-    if (k.payoff_kind != 0) shape.pairs_per_thread = 1;
-    const bool fused_exchange = fused_exchange_supported<real>(shape, k.payoff_kind, d_traj != nullptr) &&
-                                exchange_arm(comm, &ws);
-    if (pair_count > 0 || fused_exchange) {
-        CB_CUDA(launch_heston_fused<real>(k, shape, ws, d_x, d_v, d_traj, c->stream));
+    const unsigned int sig = call_signature(10u + (unsigned)k.payoff_kind + (d_traj ? 4u : 0u) + (sizeof(real) == 8 ? 8u : 0u),
+                                            seed, subsequence, R, ((uint64_t)N << 8) | (uint64_t)nK);
+    const bool fused_exchange = exchange_arm(comm, &ws, sig);
+    if (d_traj != nullptr) {
+        int threads = 0, bps = 0;
+        const bool bulk = trajectory_bulk_eligible<real>(k, d_traj, d_traj_v) && getenv("COCOS_B200_NO_BULK") == nullptr;
+        CB_CUDA((trajectory_occupancy<real>(d_traj_v != nullptr, nK > 1, bulk, &threads, &bps)));
+        CB_REQUIRE(bps >= 1, "trajectory kernel does not fit on an SM");
+        const uint64_t tiles = std::max<uint64_t>(1, (pair_count + threads - 1) / threads);
+        uint64_t blocks = std::min<uint64_t>(tiles, (uint64_t)c->sm_count * bps);
+        blocks = std::min<uint64_t>(blocks, kMaxGridBlocks);
+        if (pair_count > 0 || fused_exchange)
+            CB_CUDA((launch_heston_trajectory<real>(k, (int)blocks, bulk, ws, d_x, d_v, d_traj, d_traj_v, c->stream)));
     } else {
-        CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));   // an empty shard adds nothing
+        LaunchShape shape;
+        rc = choose_shape<real>(c, pair_count, nK > 1, k.payoff_kind, fused_exchange, &shape);
+        if (rc) return rc;
+        if (k.payoff_sign < (real)0) shape.variant = 0;
+        if (pair_count > 0 || fused_exchange)
+            CB_CUDA(launch_heston_fused<real>(k, shape, ws, d_x, d_v, c->stream));
     }
+    if (fused_exchange) exchange_commit(comm);
+    if (pair_count == 0 && !fused_exchange)
+        CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));   // an empty shard adds nothing
     if (comm != nullptr && !fused_exchange)
         CB_NCCL(g_nccl.AllReduce(c->ws.result, c->ws.result, (size_t)2 * nK, ncclDouble, ncclSum, comm->comm,
                                  c->stream));
@@ -944,7 +1000,7 @@ extern "C" CB_API int cb_heston_price_launch_f32(cb_ctx *c, const cb_heston_para
                                           uint64_t pair_first, uint64_t pair_count, cb_comm *comm, float *d_x,
                                           float *d_v, float *d_traj) {
     return heston_price_launch<float>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm, d_x,
-                                      d_v, d_traj);
+                                      d_v, d_traj, nullptr);
 }
 
 extern "C" CB_API int cb_heston_payoff_launch_f32(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
@@ -953,7 +1009,7 @@ extern "C" CB_API int cb_heston_payoff_launch_f32(cb_ctx *c, const cb_heston_par
                                                   const cb_payoff_spec *spec) {
     CB_REQUIRE(spec != nullptr, "spec is NULL");
     return heston_price_launch<float>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm,
-                                      nullptr, nullptr, nullptr, spec);
+                                      nullptr, nullptr, nullptr, nullptr, spec);
 }
 
 extern "C" CB_API int cb_heston_payoff_launch_f64(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
@@ -962,7 +1018,7 @@ extern "C" CB_API int cb_heston_payoff_launch_f64(cb_ctx *c, const cb_heston_par
                                                   const cb_payoff_spec *spec) {
     CB_REQUIRE(spec != nullptr, "spec is NULL");
     return heston_price_launch<double>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm,
-                                       nullptr, nullptr, nullptr, spec);
+                                       nullptr, nullptr, nullptr, nullptr, spec);
 }
 
 extern "C" CB_API int cb_heston_price_launch_f64(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
@@ -970,7 +1026,29 @@ extern "C" CB_API int cb_heston_price_launch_f64(cb_ctx *c, const cb_heston_para
                                           uint64_t pair_first, uint64_t pair_count, cb_comm *comm, double *d_x,
                                           double *d_v, double *d_traj) {
     return heston_price_launch<double>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm,
-                                       d_x, d_v, d_traj);
+                                       d_x, d_v, d_traj, nullptr);
+}
+
+// Path-materialising mode with both state variables: x_t into d_traj_x and v_t into d_traj_v (NULL: log prices only),
+// each [N][2*pair_count] in the [first halves | partners] layout of the shard; d_x/d_v (terminal state) are optional.
+extern "C" CB_API int cb_heston_trajectory_launch_f32(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                      const double *h_strikes, int nK, uint64_t seed,
+                                                      uint32_t subsequence, uint64_t pair_first, uint64_t pair_count,
+                                                      cb_comm *comm, float *d_x, float *d_v, float *d_traj_x,
+                                                      float *d_traj_v) {
+    CB_REQUIRE(d_traj_x != nullptr, "d_traj_x is NULL");
+    return heston_price_launch<float>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm, d_x,
+                                      d_v, d_traj_x, d_traj_v);
+}
+
+extern "C" CB_API int cb_heston_trajectory_launch_f64(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                                      const double *h_strikes, int nK, uint64_t seed,
+                                                      uint32_t subsequence, uint64_t pair_first, uint64_t pair_count,
+                                                      cb_comm *comm, double *d_x, double *d_v, double *d_traj_x,
+                                                      double *d_traj_v) {
+    CB_REQUIRE(d_traj_x != nullptr, "d_traj_x is NULL");
+    return heston_price_launch<double>(c, p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count, comm, d_x,
+                                       d_v, d_traj_x, d_traj_v);
 }
 
 extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb_heston_params *p, uint64_t R, uint32_t N,
@@ -986,13 +1064,13 @@ extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb
     const uint64_t H = (R + 1) / 2;
     CB_REQUIRE(pair_first <= H && pair_count <= H - pair_first, "pair range outside [0,%llu)", (unsigned long long)H);
     CB_REQUIRE((d_x == nullptr) == (d_v == nullptr), "d_x and d_v must both be given or both be NULL");
-    if (comm != nullptr) {
+    if (comm != nullptr && !comm->p2p) {
         rc = need_nccl();
         if (rc) return rc;
     }
     const FusedConsts<float> k = make_consts<float>(p, R, N, h_strikes, nK, seed, subsequence, pair_first, pair_count);
     ReduceWorkspace ws = c->ws;
-    const bool fused_exchange = exchange_arm(comm, &ws);
+    const bool fused_exchange = exchange_arm(comm, &ws, call_signature(3u, seed, subsequence, R, ((uint64_t)N << 8) | (uint64_t)nK));
     if (pair_count > 0 || fused_exchange) {
         const int threads = c->threads ? c->threads : 256;
         int bps = 0;
@@ -1005,6 +1083,7 @@ extern "C" CB_API int cb_heston_price_conditional_launch_f32(cb_ctx *c, const cb
         const double dt = p->T / (double)(N - 1);
         CB_CUDA(launch_heston_conditional(k, (float)p->sigma_v, (float)p->rho, (float)dt, threads, (int)blocks, ws,
                                           d_x, d_v, c->stream));
+        if (fused_exchange) exchange_commit(comm);
     } else {
         CB_CUDA(cudaMemsetAsync(c->ws.result, 0, sizeof(double) * 2 * nK, c->stream));
     }
@@ -1022,8 +1101,8 @@ extern "C" CB_API int cb_heston_price_finish(cb_ctx *c, int nK, double *h_sum, d
     CB_CUDA(cudaStreamSynchronize(c->stream));
     unsigned long long first_bits;
     memcpy(&first_bits, c->h_result, sizeof first_bits);
-    if (first_bits == kExchangeTimeoutBits)
-        return fail(CB_ERR_CUDA, "fused peer exchange timed out: a rank of the communicator never launched its shard");
+    int rc = check_exchange_poison(first_bits);
+    if (rc) return rc;
     memcpy(h_sum, c->h_result, sizeof(double) * nK);
     memcpy(h_sumsq, c->h_result + nK, sizeof(double) * nK);
     return CB_OK;
@@ -1042,9 +1121,10 @@ static int heston_price_multi(int G, cb_ctx *const *ctxs, cb_comm *const *comms,
         CB_REQUIRE(G == 1 || comms[g] != nullptr, "communicator %d is NULL", g);
     }
     const bool grouped = G > 1;
+    const bool nccl_group = grouped && !comms[0]->p2p;       // the fused exchange needs no collective library call
     const uint64_t pairs = (R + 1) / 2, per = (pairs + (uint64_t)G - 1) / (uint64_t)G;
     int rc = CB_OK;
-    if (grouped) {
+    if (nccl_group) {
         rc = cb_group_start();
         if (rc) return rc;
     }
@@ -1052,15 +1132,20 @@ static int heston_price_multi(int G, cb_ctx *const *ctxs, cb_comm *const *comms,
         const uint64_t first = std::min<uint64_t>((uint64_t)g * per, pairs);
         const uint64_t count = std::min<uint64_t>(per, pairs - first);
         rc = heston_price_launch<real>(ctxs[g], p, R, N, h_strikes, nK, seed, subsequence, first, count,
-                                       grouped ? comms[g] : nullptr, nullptr, nullptr, nullptr, spec);
+                                       grouped ? comms[g] : nullptr, nullptr, nullptr, nullptr, nullptr, spec);
     }
-    if (grouped) {
+    if (nccl_group) {
         const int rc_end = cb_group_end();          // always close the group, keep the first error
         if (rc == CB_OK) rc = rc_end;
     }
     if (rc) return rc;
-    rc = cb_heston_price_finish(ctxs[0], nK, h_sum, h_sumsq);   // every rank holds the reduced sums
-    for (int g = 1; g < G && rc == CB_OK; ++g) rc = cb_ctx_sync(ctxs[g]);
+    // every rank holds the reduced sums; each one is read back so that a rank whose exchange failed (poison value)
+    // is reported, not just rank 0's.  The first context's copy is the one returned.
+    double other_sum[CB_MAX_STRIKES], other_sq[CB_MAX_STRIKES];
+    for (int g = G - 1; g >= 0; --g) {
+        const int rc_g = cb_heston_price_finish(ctxs[g], nK, g == 0 ? h_sum : other_sum, g == 0 ? h_sumsq : other_sq);
+        if (rc == CB_OK) rc = rc_g;
+    }
     return rc;
 }
 
@@ -1107,13 +1192,22 @@ extern "C" CB_API int cb_pi_count_launch(cb_ctx *c, uint64_t n, uint64_t seed, u
     const uint64_t ndraw = antithetic ? (n + 1) / 2 : n;
     CB_REQUIRE(draw_first <= ndraw && draw_count <= ndraw - draw_first, "draw range outside [0,%llu)",
                (unsigned long long)ndraw);
-    if (comm != nullptr) {
+    const bool p2p = comm != nullptr && comm->p2p;
+    if (comm != nullptr && !p2p) {
         int rc = need_nccl();
         if (rc) return rc;
     }
+    int &bps = c->pi_blocks_per_sm[antithetic ? 1 : 0];
+    if (bps == 0) {
+        CB_CUDA(pi_occupancy(antithetic, &bps));
+        CB_REQUIRE(bps >= 1, "pi kernel does not fit on an SM");
+    }
+    ReduceWorkspace ws = c->ws;
+    const bool fused_exchange = exchange_arm(comm, &ws, call_signature(antithetic ? 2u : 1u, seed, subsequence, n, 0));
     CB_CUDA(launch_pi_count(n, antithetic, draw_first, draw_count, philox_keys_from_seed(seed), subsequence,
-                            c->d_inside, c->sm_count, c->stream));
-    if (comm != nullptr)
+                            c->d_inside, c->sm_count * bps, ws, c->stream));
+    if (fused_exchange) exchange_commit(comm);
+    if (comm != nullptr && !fused_exchange)
         CB_NCCL(g_nccl.AllReduce(c->d_inside, c->d_inside, 1, ncclUint64, ncclSum, comm->comm, c->stream));
     return CB_OK;
 }
@@ -1124,6 +1218,8 @@ extern "C" CB_API int cb_pi_count_finish(cb_ctx *c, uint64_t *h_inside) {
     unsigned long long *h = reinterpret_cast<unsigned long long *>(c->h_result + kMaxAcc);
     CB_CUDA(cudaMemcpyAsync(h, c->d_inside, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CB_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = check_exchange_poison(*h);
+    if (rc) return rc;
     *h_inside = *h;
     return CB_OK;
 }
@@ -1137,9 +1233,10 @@ extern "C" CB_API int cb_pi_count_multi(int G, cb_ctx *const *ctxs, cb_comm *con
         CB_REQUIRE(G == 1 || comms[g] != nullptr, "communicator %d is NULL", g);
     }
     const bool grouped = G > 1;
+    const bool nccl_group = grouped && !comms[0]->p2p;
     const uint64_t ndraw = antithetic ? (n + 1) / 2 : n, per = (ndraw + (uint64_t)G - 1) / (uint64_t)G;
     int rc = CB_OK;
-    if (grouped) {
+    if (nccl_group) {
         rc = cb_group_start();
         if (rc) return rc;
     }
@@ -1148,11 +1245,15 @@ extern "C" CB_API int cb_pi_count_multi(int G, cb_ctx *const *ctxs, cb_comm *con
         rc = cb_pi_count_launch(ctxs[g], n, seed, subsequence, antithetic, first, std::min<uint64_t>(per, ndraw - first),
                                 grouped ? comms[g] : nullptr);
     }
-    if (grouped) {
+    if (nccl_group) {
         const int rc_end = cb_group_end();
         if (rc == CB_OK) rc = rc_end;
     }
-    for (int g = G - 1; g >= 0 && rc == CB_OK; --g) rc = cb_pi_count_finish(ctxs[g], h_inside);
+    if (rc) return rc;
+    for (int g = G - 1; g >= 0; --g) {                       // every rank is read: a failed exchange anywhere is reported
+        const int rc_g = cb_pi_count_finish(ctxs[g], h_inside);
+        if (rc == CB_OK) rc = rc_g;
+    }
     return rc;
 }
 
@@ -1161,7 +1262,7 @@ extern "C" CB_API int cb_pi_count_multi(int G, cb_ctx *const *ctxs, cb_comm *con
 extern "C" CB_API int cb_peak_measure(cb_ctx *c, int kind, int repeats, double *ops_per_s, float *ms_best) {
     CB_CTX(c);
     CB_REQUIRE(ops_per_s != nullptr, "ops_per_s is NULL");
-    CB_REQUIRE(kind >= 0 && kind <= 20, "kind must be in [0,20]");
+    CB_REQUIRE(kind >= 0 && kind <= 38, "kind must be in [0,38]");
     if (repeats < 1) repeats = 1;
     size_t bytes = 4096;
     if (kind == 8 || kind == 10) bytes = (size_t)4 << 30;   // far larger than the 126 MB L2

@@ -52,17 +52,23 @@ struct FusedConsts {
 // mappings, raises its flag there (release, system scope), waits until all ranks' flags have arrived on its own
 // device (acquire) and folds the slots in rank order -- every rank ends with the same bits in `result`.
 // Two slot parities make the next launch's writes safe: a rank can only be one launch ahead of the slowest one.
+// Every slot carries a tag (launch number and element count of the data it holds) that the folding rank verifies:
+// ranks whose launch counters have drifted apart (a failed launch on one of them, mismatched calls) end with the
+// poison value in `result` instead of a silently wrong sum.
 constexpr int kMaxPeers = 8;
+constexpr int kSlotStride = kMaxAcc + 2;   // kMaxAcc values + the tag (+ padding to 16 bytes), in 8-byte words
 struct PeerExchange {
     int nranks;                       // < 2: no exchange
     int rank;
-    double *slots[kMaxPeers];         // rank p's buffer, mapped here: [2][kMaxPeers][kMaxAcc]
+    unsigned long long *slots[kMaxPeers];   // rank p's buffer, mapped here: [2][kMaxPeers][kSlotStride]
     unsigned int *flags[kMaxPeers];   // rank p's flags, mapped here: [kMaxPeers], flags[r] = last epoch published by r
 };
-constexpr size_t kExchangeSlotBytes = sizeof(double) * 2 * kMaxPeers * kMaxAcc;
+constexpr size_t kExchangeSlotBytes = sizeof(unsigned long long) * 2 * kMaxPeers * kSlotStride;
 constexpr size_t kExchangeBytes = kExchangeSlotBytes + sizeof(unsigned int) * kMaxPeers;
-// what `result` holds when a peer never showed up (a quiet NaN with a recognisable payload)
+// what `result` holds when a peer never showed up or its slot carried another launch's tag (quiet NaNs with
+// recognisable payloads; as integers they are far above any possible count)
 constexpr unsigned long long kExchangeTimeoutBits = 0x7FF8C0C05B200DEAull;
+constexpr unsigned long long kExchangeMismatchBits = 0x7FF8C0C05B200BADull;
 
 struct ReduceWorkspace {
     double *partials;    // [kMaxGridBlocks][kMaxAcc]
@@ -72,18 +78,30 @@ struct ReduceWorkspace {
     // of kernel parameters instead of the table itself, read by the last block only -- and this launch's number
     const PeerExchange *px;
     unsigned int epoch;  // launch number on the communicator (> 0), identical on every rank
+    unsigned int sig;    // signature of the call (kind, seed, subsequence, sizes): ranks must agree on it, the slots' tags carry it
 };
 
 template <typename real>
 cudaError_t launch_heston_fused(const FusedConsts<real> &c, const LaunchShape &shape, ReduceWorkspace ws,
-                                real *d_x, real *d_v, real *d_traj, cudaStream_t stream);
+                                real *d_x, real *d_v, cudaStream_t stream);
 
-// true when launch_heston_fused has an instantiation with the fused cross-GPU exchange for this launch
+// true when launch_heston_fused has an instantiation with the fused cross-GPU exchange for this geometry
 template <typename real>
-bool fused_exchange_supported(const LaunchShape &shape, int payoff_kind, bool traj);
+bool fused_exchange_supported(const LaunchShape &shape, int payoff_kind);
 
+// occupancy and register count of the instantiation launch_heston_fused would pick (xchg: with the fused exchange)
 template <typename real>
-cudaError_t fused_occupancy(int threads, int pairs_per_thread, bool multi, int variant, int *blocks_per_sm, int *regs);
+cudaError_t fused_occupancy(int threads, int pairs_per_thread, bool multi, int payoff_kind, int variant, bool xchg,
+                            int *blocks_per_sm, int *regs);
+
+// path-materialising kernel (heston_trajectory.cu): every step of x (and v when d_traj_v != NULL) goes to HBM
+template <typename real>
+bool trajectory_bulk_eligible(const FusedConsts<real> &c, const real *d_traj_x, const real *d_traj_v);
+template <typename real>
+cudaError_t trajectory_occupancy(bool with_v, bool multi, bool bulk, int *threads, int *blocks_per_sm);
+template <typename real>
+cudaError_t launch_heston_trajectory(const FusedConsts<real> &c, int blocks, bool bulk, ReduceWorkspace ws,
+                                     real *d_x, real *d_v, real *d_traj_x, real *d_traj_v, cudaStream_t stream);
 
 // conditional-Gaussian scheme (heston_conditional.cu)
 cudaError_t launch_heston_conditional(const FusedConsts<float> &c, float sigma_v, float rho, float dt, int threads,
@@ -136,7 +154,8 @@ cudaError_t launch_kde_evaluate(const float *d_p, const float *d_w, uint64_t n, 
 // Monte-Carlo pi
 cudaError_t launch_pi_count(uint64_t n, int antithetic, uint64_t draw_first, uint64_t draw_count,
                             const PhiloxKeys &k, uint32_t subseq, unsigned long long *d_inside,
-                            int sm_count, cudaStream_t s);
+                            int resident_blocks, ReduceWorkspace ws, cudaStream_t s);
+cudaError_t pi_occupancy(int antithetic, int *blocks_per_sm);
 
 // calibration
 cudaError_t launch_peak_kernel(int kind, int sm_count, void *d_scratch, size_t scratch_bytes, double *work_done,

@@ -16,6 +16,70 @@ namespace cb {
 constexpr int kFusedMaxThreads = 256;
 constexpr int kFusedMaxWarps = kFusedMaxThreads / 32;
 
+// The fused cross-GPU step (see PeerExchange in kernels.h).  Runs in the LAST block of a launch only, after
+// result[0..n) holds this rank's totals (doubles, or 64-bit counts for the pi kernel).  On return every rank holds
+// the rank-ordered sum in result[] -- identical bits everywhere -- or a poison value when a peer never arrived
+// (watchdog on the wall clock, %globaltimer: 60 s) or published another launch's data (tag mismatch).
+// A real call, not inlined: the time loop of the calling kernel keeps the schedule it has without this code.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long as_word(double v) { return (unsigned long long)__double_as_longlong(v); }
+__device__ __forceinline__ unsigned long long as_word(unsigned long long v) { return v; }
+template <typename T> __device__ __forceinline__ T from_word(unsigned long long w);
+template <> __device__ __forceinline__ double from_word<double>(unsigned long long w) { return __longlong_as_double((long long)w); }
+template <> __device__ __forceinline__ unsigned long long from_word<unsigned long long>(unsigned long long w) { return w; }
+
+constexpr unsigned long long kExchangeWatchdogNs = 60ull * 1000000000ull;
+
+template <typename T>
+static __device__ __noinline__ void peer_exchange_fold(int n, T *result, const PeerExchange *table, unsigned int epoch,
+                                                       unsigned int sig) {
+    const PeerExchange &px = *table;
+    const size_t parity_base = (size_t)(epoch & 1u) * kMaxPeers * kSlotStride;
+    const unsigned long long tag = ((unsigned long long)(sig & 0xFFFFFFu) << 40) | ((unsigned long long)(n & 0xFF) << 32) | epoch;
+    __syncthreads();                                        // result[] was written by threads of this block
+    for (int a = threadIdx.x; a <= n; a += blockDim.x) {    // element n of a slot is its tag
+        const unsigned long long w = a < n ? as_word(result[a]) : tag;
+        const size_t at = parity_base + (size_t)px.rank * kSlotStride + (a < n ? a : kMaxAcc);
+        for (int p = 0; p < px.nranks; ++p) px.slots[p][at] = w;
+    }
+    __threadfence_system();                                 // the slots are out before any flag is
+    __syncthreads();
+    __shared__ int s_fault;                                 // 0 fine, 1 timed out, 2 tag mismatch
+    if (threadIdx.x == 0) s_fault = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < px.nranks) {
+        unsigned int *remote = px.flags[threadIdx.x] + px.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+        const unsigned int *mine = px.flags[px.rank] + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        for (;;) {
+            unsigned int seen;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if ((int)(seen - epoch) >= 0) break;
+            if (global_timer_ns() - t0 > kExchangeWatchdogNs) { atomicMax(&s_fault, 1); break; }   // a rank never launched
+            __nanosleep(64);
+        }
+        // the slot of rank threadIdx.x must hold THIS launch (same number, same element count)
+        const unsigned long long got =
+            __ldcg(px.slots[px.rank] + parity_base + (size_t)threadIdx.x * kSlotStride + kMaxAcc);
+        if (got != tag) atomicMax(&s_fault, 2);
+    }
+    __syncthreads();
+    const int fault = s_fault;
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        T t = (T)0;
+        for (int r = 0; r < px.nranks; ++r)
+            t += from_word<T>(__ldcg(px.slots[px.rank] + parity_base + (size_t)r * kSlotStride + a));
+        if (fault == 1) t = from_word<T>(kExchangeTimeoutBits);
+        else if (fault == 2) t = from_word<T>(kExchangeMismatchBits);
+        result[a] = t;
+    }
+}
+
 template <typename real, bool MULTI>
 struct PayoffAccumulator {
     double sum[MULTI ? 2 : 1] = {};
@@ -136,45 +200,7 @@ struct PayoffAccumulator {
         }
         if (threadIdx.x == 0) *ws.ticket = 0u;   // ready for the next launch on this stream
         if constexpr (XCHG) {
-            if (ws.px != nullptr) exchange(nacc, ws.result, ws.px, ws.epoch);
-        }
-    }
-
-    // The fused cross-GPU step (see PeerExchange); runs in the last block only, after ws.result holds this rank's totals.
-    // (a real call, not inlined: the time loop of the kernel keeps the schedule it has without this code)
-    static __device__ __noinline__ void exchange(int nacc, double *result, const PeerExchange *table, unsigned int epoch) {
-        const PeerExchange &px = *table;
-        const size_t parity_base = (size_t)(epoch & 1u) * kMaxPeers * kMaxAcc;
-        __syncthreads();                                        // result[] was written by threads of this block
-        for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
-            const double t = result[a];
-            for (int p = 0; p < px.nranks; ++p) px.slots[p][parity_base + (size_t)px.rank * kMaxAcc + a] = t;
-        }
-        __threadfence_system();                                 // the slots are out before any flag is
-        __syncthreads();
-        __shared__ int s_timed_out;
-        if (threadIdx.x == 0) s_timed_out = 0;
-        __syncthreads();
-        if ((int)threadIdx.x < px.nranks) {
-            unsigned int *remote = px.flags[threadIdx.x] + px.rank;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
-            const unsigned int *mine = px.flags[px.rank] + threadIdx.x;
-            const long long t0 = clock64();
-            for (;;) {
-                unsigned int seen;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-                if ((int)(seen - epoch) >= 0) break;
-                if (clock64() - t0 > 120000000000ll) { s_timed_out = 1; break; }  // ~60 s: a rank never launched
-                __nanosleep(64);
-            }
-        }
-        __syncthreads();
-        const bool dead = s_timed_out != 0;
-        for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
-            double t = 0.0;
-            for (int r = 0; r < px.nranks; ++r)
-                t += __ldcg(px.slots[px.rank] + parity_base + (size_t)r * kMaxAcc + a);
-            result[a] = dead ? __longlong_as_double((long long)kExchangeTimeoutBits) : t;
+            if (ws.px != nullptr) peer_exchange_fold<double>(nacc, ws.result, ws.px, ws.epoch, ws.sig);
         }
     }
 };

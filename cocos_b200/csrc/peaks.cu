@@ -182,6 +182,61 @@ peak_ffma2_kernel(float *out, float fa, float fb, uint32_t m0) {
     if (s == 123.456f || t == 0x12345678u) out[0] = s;
 }
 
+// Pipe-model probes (round 2): per chain and trip W half Philox rounds (IMAD.WIDE.U32 + three-input XOR),
+// F FFMA on three DISTINCT registers, L three-register LOP3 of a nonlinear feedback register, A FADD --
+// every group on its own independent chains.  Timing the mixes tells which instructions share a pipe and what an
+// IMAD.WIDE really costs next to FP32 and logic work (the Philox round is 2 WIDE + 2 LOP3).
+template <int W, int F, int L, int A>
+__global__ void __launch_bounds__(256)
+peak_mix_kernel(uint32_t *out, uint32_t m0, float fa, float fb) {
+    unsigned long long xw[kChains];
+    float xf[kChains], yf[kChains], zf[kChains], xa[kChains];
+    uint32_t xl[kChains], yl[kChains], zl[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        xw[i] = ((unsigned long long)(threadIdx.x * 2654435761u + i) << 32) | (threadIdx.x + 77u * i);
+        xf[i] = 1.0f + 0.001f * (float)(threadIdx.x + i);
+        yf[i] = fa + 1e-7f * (float)(i + threadIdx.x);
+        zf[i] = fb * (float)(i + 1 + threadIdx.x);
+        xa[i] = 0.5f * (float)(i + threadIdx.x);
+        xl[i] = threadIdx.x * 40503u + i;
+        yl[i] = m0 ^ (0x01010101u * (i + threadIdx.x));
+        zl[i] = m0 + i * 977u + threadIdx.x;
+    }
+#pragma unroll 1
+    for (int it = 0; it < kIters; it += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) {
+#pragma unroll
+                for (int w = 0; w < W; ++w) {    // half a Philox round: one IMAD.WIDE + one three-input XOR
+                    const unsigned long long p = (unsigned long long)(uint32_t)xw[i] * m0;
+                    xw[i] = (uint32_t)(p >> 32) ^ (uint32_t)p ^ yl[(i + 3) % kChains];
+                }
+#pragma unroll
+                for (int f = 0; f < F; ++f) xf[i] = fmaf(xf[i], yf[i], zf[i]);
+#pragma unroll
+                for (int l = 0; l < L; ++l) {    // nonlinear feedback: ptxas cannot collapse consecutive steps
+                    const uint32_t t = (xl[i] & yl[i]) ^ zl[i];
+                    xl[i] = yl[i];
+                    yl[i] = zl[i];
+                    zl[i] = t;
+                }
+#pragma unroll
+                for (int a = 0; a < A; ++a) xa[i] = xa[i] + yf[i];
+            }
+    }
+    uint32_t s = 0;
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        s ^= (uint32_t)xw[i] ^ xl[i] ^ yl[i] ^ zl[i];
+        t += xf[i] + xa[i];
+    }
+    if (s == 0x12345678u || t == 123.456f) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256)
 peak_hbm_write_kernel(float4 *out, size_t n_vec) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -239,6 +294,27 @@ cudaError_t launch_peak_kernel(int kind, int sm_count, void *d_scratch, size_t s
         case 18: peak_ffma2_kernel<0><<<grid, threads, 0, s>>>((float *)d_scratch, 1.000001f, 1e-7f, 0x9E3779B9u); *work_done = thread_ops; break;
         case 19: peak_ffma2_kernel<1><<<grid, threads, 0, s>>>((float *)d_scratch, 1.000001f, 1e-7f, 0x9E3779B9u); *work_done = thread_ops; break;
         case 20: peak_ffma2_kernel<2><<<grid, threads, 0, s>>>((float *)d_scratch, 1.000001f, 1e-7f, 0x9E3779B9u); *work_done = thread_ops; break;
+#define CB_MIX(K, W, F, L, A) \
+        case K: peak_mix_kernel<W, F, L, A><<<grid, threads, 0, s>>>((uint32_t *)d_scratch, 0xD2511F53u, 1.000001f, 1e-7f); *work_done = thread_ops; break;
+        CB_MIX(21, 1, 0, 0, 0)   // IMAD.WIDE alone
+        CB_MIX(22, 0, 1, 0, 0)   // FFMA, three distinct registers
+        CB_MIX(23, 0, 0, 1, 0)   // LOP3, three registers
+        CB_MIX(24, 0, 0, 0, 1)   // FADD
+        CB_MIX(25, 1, 0, 1, 0)   // the Philox mix: WIDE + LOP3
+        CB_MIX(26, 1, 0, 2, 0)
+        CB_MIX(27, 1, 0, 4, 0)
+        CB_MIX(28, 1, 1, 0, 0)   // WIDE + FFMA
+        CB_MIX(29, 1, 2, 0, 0)
+        CB_MIX(30, 1, 4, 0, 0)
+        CB_MIX(31, 0, 1, 1, 0)   // FFMA + LOP3: two pipes
+        CB_MIX(32, 0, 2, 1, 0)
+        CB_MIX(33, 0, 1, 2, 0)
+        CB_MIX(34, 1, 1, 1, 0)   // all three
+        CB_MIX(35, 1, 2, 2, 0)
+        CB_MIX(36, 0, 1, 0, 1)   // FFMA + FADD: same pipe?
+        CB_MIX(37, 1, 0, 0, 1)   // WIDE + FADD
+        CB_MIX(38, 1, 0, 0, 2)
+#undef CB_MIX
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

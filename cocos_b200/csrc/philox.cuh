@@ -119,6 +119,54 @@ struct PairStream {
     }
 };
 
+// Philox4x32-10 for counters (c0, hi, 0, subsequence) with everything but c0 uniform: rounds 0 and 1 cost one
+// multiply each.  Bit-identical to philox4x32_10(c0, hi, 0, subsequence, k).
+struct UniformTail {
+    uint32_t x0;        // subsequence ^ k1[0]           n2 of round 0 = hi(M0*c0) ^ x0
+    uint32_t x1;        // hi(M0*A) ^ k1[1]              n2 of round 1 = lo(M0*c0) ^ x1,   A = hi ^ k0[0]
+    uint32_t k01;       // k0[1]                         n0 of round 1 = hi(M1*n2) ^ k01   (c1 entering round 1 is 0)
+    uint32_t x2;        // lo(M0*A) ^ k1[2]              n2 of round 2 = hi(M0*n0') ^ x2
+    __device__ __forceinline__ void init(uint32_t hi, uint32_t subsequence, const PhiloxKeys &k) {
+        const uint32_t A = hi ^ k.k0[0];
+        const uint64_t pa = (uint64_t)kPhiloxM0 * A;
+        x0 = pin(subsequence ^ k.k1[0]);
+        x1 = pin((uint32_t)(pa >> 32) ^ k.k1[1]);
+        k01 = pin(k.k0[1]);
+        x2 = pin((uint32_t)pa ^ k.k1[2]);
+    }
+    __device__ __forceinline__ uint4 call(uint32_t c0, const PhiloxKeys &k) const {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;                    // round 0
+        const uint32_t a2 = (uint32_t)(p0 >> 32) ^ x0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * a2;                    // round 1
+        uint32_t c0r = (uint32_t)(p1 >> 32) ^ k01;
+        uint32_t c2r = (uint32_t)p0 ^ x1;
+        uint32_t c1r = (uint32_t)p1;
+        uint32_t c3r;
+        {                                                                // round 2: c3 entering it is uniform
+            const uint64_t q0 = (uint64_t)kPhiloxM0 * c0r;
+            const uint64_t q1 = (uint64_t)kPhiloxM1 * c2r;
+            const uint32_t m0 = (uint32_t)(q1 >> 32) ^ c1r ^ k.k0[2];
+            const uint32_t m2 = (uint32_t)(q0 >> 32) ^ x2;
+            c1r = (uint32_t)q1;
+            c3r = (uint32_t)q0;
+            c0r = m0;
+            c2r = m2;
+        }
+#pragma unroll
+        for (int r = 3; r < 10; ++r) {
+            const uint64_t q0 = (uint64_t)kPhiloxM0 * c0r;
+            const uint64_t q1 = (uint64_t)kPhiloxM1 * c2r;
+            const uint32_t m0 = (uint32_t)(q1 >> 32) ^ c1r ^ k.k0[r];
+            const uint32_t m2 = (uint32_t)(q0 >> 32) ^ c3r ^ k.k1[r];
+            c1r = (uint32_t)q1;
+            c3r = (uint32_t)q0;
+            c0r = m0;
+            c2r = m2;
+        }
+        return make_uint4(c0r, c1r, c2r, c3r);
+    }
+};
+
 // float in [1,2) from the high 23 bits: one LEA.HI (shift + add), no I2F (I2F
 // shares the quarter-rate XU pipe with MUFU, the pipe this workload is bound by).
 __device__ __forceinline__ float mantissa_float(uint32_t o) {

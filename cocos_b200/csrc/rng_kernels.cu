@@ -12,6 +12,10 @@
 //   f64: elements 2j, 2j+1 from Philox(index=j): uniform u52(o0,o1), u52(o2,o3);
 //        normal: one Box-Muller pair from U = 1-u52(o0,o1), t = u52(o2,o3)
 // Each thread produces 16 bytes per Philox call and stores them as one vector.
+#include <map>
+#include <mutex>
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace cb {
@@ -91,6 +95,63 @@ random_fill_kernel(real *__restrict__ out, uint64_t n, const __grid_constant__ P
     }
 }
 
+// The fast path of random_fill_kernel for a 16-byte aligned output: same elements, but
+//   * rounds 0 and 1 of Philox cost one multiply each (UniformTail: three of the four counter words are uniform),
+//     round keys live in registers;
+//   * the 64-bit block index is cut into segments with a uniform high word, inside which a thread owns the blocks
+//     first + gtid + t*stride: 32-bit arithmetic, a trip count known up front, no bounds test per block and one
+//     64-bit pointer bump per trip; two Philox calls per trip are independent chains for the scheduler;
+//   * the ragged last block (n not a multiple of W) is written by one thread with scalar stores.
+template <typename real, bool NORMAL>
+__global__ void __launch_bounds__(256)
+random_fill_fast_kernel(real *__restrict__ out, uint64_t n, const __grid_constant__ PhiloxKeys kc, uint32_t subseq) {
+    using D = Draw<real, NORMAL>;
+    constexpr int W = D::W;
+    using vec_t = typename std::conditional<W == 4, float4, double2>::type;
+    PhiloxKeys k;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { k.k0[r] = pin(kc.k0[r]); k.k1[r] = pin(kc.k1[r]); }
+    const uint64_t full = n / W;                              // whole blocks: one 16-byte vector each
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    auto store = [](vec_t *dst, const real (&v)[W]) {
+        if constexpr (W == 4) __stcs(dst, make_float4(v[0], v[1], v[2], v[3]));
+        else __stcs(dst, make_double2(v[0], v[1]));
+    };
+    for (uint64_t seg = 0; seg < full;) {
+        const uint32_t hi = (uint32_t)(seg >> 32);
+        const uint64_t seg_end = ((uint64_t)hi + 1) << 32 < full ? ((uint64_t)hi + 1) << 32 : full;
+        const uint64_t span = seg_end - seg;
+        UniformTail tail;
+        tail.init(hi, subseq, k);
+        const uint64_t mine = span > gtid ? (span - gtid + stride - 1) / stride : 0;
+        uint32_t c0 = (uint32_t)seg + gtid;
+        vec_t *dst = reinterpret_cast<vec_t *>(out) + seg + gtid;
+        for (uint32_t t = (uint32_t)(mine >> 1); t > 0; --t) {
+            real va[W], vb[W];
+            const uint4 a = tail.call(c0, k);
+            const uint4 b = tail.call(c0 + stride, k);
+            D::make(a, va);
+            D::make(b, vb);
+            store(dst, va);
+            store(dst + stride, vb);
+            c0 += 2u * stride;
+            dst += 2ull * stride;
+        }
+        if (mine & 1) {
+            real va[W];
+            D::make(tail.call(c0, k), va);
+            store(dst, va);
+        }
+        seg = seg_end;
+    }
+    if (gtid == 0 && full * W < n) {                          // the ragged last block
+        real v[W];
+        D::make(philox4x32_10((uint32_t)full, (uint32_t)(full >> 32), 0u, subseq, k), v);
+        for (int e = 0; e < W; ++e) if (full * W + e < n) out[full * W + e] = v[e];
+    }
+}
+
 // Output shape (outer, d, inner) row-major, antithetic along the middle axis:
 // draws fill [.., 0:ceil(d/2), ..] in draw order (flattened (outer, ceil(d/2), inner)),
 // reflections fill [.., ceil(d/2):d, ..].
@@ -143,46 +204,69 @@ random_antithetic_kernel(real *__restrict__ out, uint64_t outer, uint64_t d, uin
 }
 
 // float32 normals, six per Philox block: the three (23-bit radius, 19-bit angle) draws of the fused Heston kernel
-// (the Philox call, ~100 issue cycles, is what bounds these fills, so the block is used to the last bit).
-// A warp produces 192 consecutive floats; they are transposed through shared memory so that the global stores
-// are 16-byte vectors covering 768 contiguous bytes.
-__global__ void __launch_bounds__(256)
-randn6_fill_kernel(float *__restrict__ out, uint64_t n, const __grid_constant__ PhiloxKeys k, uint32_t subseq) {
-    __shared__ __align__(16) float s_tile[8][192];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t n_blocks = (n + 5) / 6;
-    const uint64_t n_tiles = (n_blocks + 31) / 32;
-    const uint64_t warps_total = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += warps_total) {
-        const uint64_t j = tile * 32 + lane;
-        const uint4 o = philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, subseq, k);
-        float v[6];
-        const uint32_t w[3] = {o.x, o.y, o.z};
+// (the Philox call is what bounds these fills, so the block is used to the last bit).
+// A warp produces 192 consecutive floats per tile (32 blocks); they are transposed through shared memory so that the
+// global stores are 16-byte vectors covering 768 contiguous bytes.  Like the other fills: UniformTail rounds, keys
+// in registers, 32-bit tile arithmetic inside segments with a uniform high counter word, no bounds test per tile --
+// the last, ragged tile of the array is written by one warp with scalar stores.
+__device__ __forceinline__ void randn6_draws(const uint4 &o, float (&v)[6]) {
+    const uint32_t w[3] = {o.x, o.y, o.z};
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const uint32_t field = (__funnelshift_l(o.w << (10 * d), w[d], 14) & 0x007FFFF0u) | 0x3F800000u;
-            const float r = mufu_sqrt(mufu_lg2(2.0f - mantissa_float(w[d])) * -1.3862943611198906f);
-            const float theta = fmaf(__uint_as_float(field), kTwoPi, -kThreePi);
-            v[2 * d] = r * mufu_cos(theta);
-            v[2 * d + 1] = r * mufu_sin(theta);
+    for (int d = 0; d < 3; ++d) {
+        const uint32_t field = (__funnelshift_l(o.w << (10 * d), w[d], 14) & 0x007FFFF0u) | 0x3F800000u;
+        const float r = mufu_sqrt(mufu_lg2(2.0f - mantissa_float(w[d])) * -1.3862943611198906f);
+        const float theta = fmaf(__uint_as_float(field), kTwoPi, -kThreePi);
+        v[2 * d] = r * mufu_cos(theta);
+        v[2 * d + 1] = r * mufu_sin(theta);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+randn6_fill_kernel(float *__restrict__ out, uint64_t n, const __grid_constant__ PhiloxKeys kc, uint32_t subseq) {
+    __shared__ __align__(16) float s_tile[8][192];
+    PhiloxKeys k;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { k.k0[r] = pin(kc.k0[r]); k.k1[r] = pin(kc.k1[r]); }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + warp;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const uint64_t full_tiles = aligned ? n / 192 : 0;        // tiles written with vector stores
+    float2 *mine = reinterpret_cast<float2 *>(&s_tile[warp][lane * 6]);
+    const float4 *src = reinterpret_cast<const float4 *>(s_tile[warp]);
+    // segments of 2^27 tiles share the high word of the block index (block = 32*tile + lane)
+    for (uint64_t seg = 0; seg < full_tiles;) {
+        const uint32_t hi = (uint32_t)(seg >> 27);
+        const uint64_t seg_end = ((uint64_t)hi + 1) << 27 < full_tiles ? ((uint64_t)hi + 1) << 27 : full_tiles;
+        const uint64_t span = seg_end - seg;
+        UniformTail tail;
+        tail.init(hi, subseq, k);
+        const uint32_t trips = span > gwarp ? (uint32_t)((span - gwarp + nwarps - 1) / nwarps) : 0;
+        uint32_t c0 = (uint32_t)((seg + gwarp) << 5) + lane;
+        float4 *dst = reinterpret_cast<float4 *>(out + (seg + gwarp) * 192) + lane;
+        for (uint32_t t = trips; t > 0; --t) {
+            float v[6];
+            randn6_draws(tail.call(c0, k), v);
+            mine[0] = make_float2(v[0], v[1]);
+            mine[1] = make_float2(v[2], v[3]);
+            mine[2] = make_float2(v[4], v[5]);
+            __syncwarp();
+            __stcs(dst, src[lane]);
+            if (lane < 16) __stcs(dst + 32, src[32 + lane]);
+            __syncwarp();
+            c0 += nwarps << 5;
+            dst += (size_t)nwarps * 48;
         }
-        float2 *mine = reinterpret_cast<float2 *>(&s_tile[warp][lane * 6]);
-        mine[0] = make_float2(v[0], v[1]);
-        mine[1] = make_float2(v[2], v[3]);
-        mine[2] = make_float2(v[4], v[5]);
-        __syncwarp();
-        const uint64_t base = tile * 192;
-        if (aligned && base + 192 <= n) {
-            const float4 *src = reinterpret_cast<const float4 *>(s_tile[warp]);
-            float4 *dst = reinterpret_cast<float4 *>(out + base);
-            __stcs(dst + lane, src[lane]);
-            if (lane < 16) __stcs(dst + 32 + lane, src[32 + lane]);
-        } else {
-            for (uint32_t e = lane; e < 192; e += 32)
-                if (base + e < n) out[base + e] = s_tile[warp][e];
-        }
-        __syncwarp();
+        seg = seg_end;
+    }
+    // what the vector path did not cover: the ragged end (or everything, for an unaligned output)
+    const uint64_t n_blocks = (n + 5) / 6;
+    const uint64_t first_block = full_tiles * 32;
+    for (uint64_t j = first_block + (uint64_t)gwarp * 32 + lane; j < n_blocks; j += (uint64_t)nwarps * 32) {
+        float v[6];
+        randn6_draws(philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, subseq, k), v);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) if (j * 6 + e < n) out[j * 6 + e] = v[e];
     }
 }
 
@@ -191,6 +275,27 @@ static int fill_grid(uint64_t n_blocks) {
     if (b < 1) b = 1;
     const uint64_t cap = 148ull * 8 * 4;
     return (int)(b > cap ? cap : b);
+}
+
+// grid of the fast fills: every block the device can hold at once (occupancy query, cached per kernel), each thread
+// then walks its strided share of the Philox blocks
+static int resident_grid(const void *fn, uint64_t blocks_wanted) {
+    static std::map<const void *, int> cache;
+    static std::mutex lock;
+    int resident = 0;
+    {
+        std::lock_guard<std::mutex> g(lock);
+        auto it = cache.find(fn);
+        if (it == cache.end()) {
+            int dev = 0, sms = 148, bps = 8;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 256, 0) != cudaSuccess || bps < 1) bps = 1;
+            it = cache.emplace(fn, sms * bps).first;
+        }
+        resident = it->second;
+    }
+    if (blocks_wanted < 1) blocks_wanted = 1;
+    return (int)(blocks_wanted < (uint64_t)resident ? blocks_wanted : (uint64_t)resident);
 }
 
 cudaError_t launch_philox_words(uint32_t *d_out, uint64_t n_blocks, uint64_t first, uint32_t block,
@@ -206,12 +311,18 @@ cudaError_t launch_random_fill(real *d_out, uint64_t n, const PhiloxKeys &k, uin
     if (n == 0) return cudaSuccess;
     if constexpr (NORMAL && sizeof(real) == 4) {
         const uint64_t tiles = ((n + 5) / 6 + 31) / 32;
-        const uint64_t cap = 148ull * 8;
-        const uint64_t blocks = (tiles + 7) / 8;
-        randn6_fill_kernel<<<(int)(blocks < cap ? (blocks ? blocks : 1) : cap), 256, 0, s>>>(d_out, n, k, subseq);
+        randn6_fill_kernel<<<resident_grid((const void *)randn6_fill_kernel, (tiles + 7) / 8), 256, 0, s>>>(d_out, n, k,
+                                                                                                          subseq);
         return cudaGetLastError();
     }
     constexpr int W = Draw<real, NORMAL>::W;
+    if ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+        const void *fn = (const void *)random_fill_fast_kernel<real, NORMAL>;
+        // two blocks per thread and trip
+        random_fill_fast_kernel<real, NORMAL><<<resident_grid(fn, ((n + W - 1) / W + 511) / 512), 256, 0, s>>>(
+            d_out, n, k, subseq);
+        return cudaGetLastError();
+    }
     random_fill_kernel<real, NORMAL><<<fill_grid((n + W - 1) / W), 256, 0, s>>>(d_out, n, k, subseq);
     return cudaGetLastError();
 }

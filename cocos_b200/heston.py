@@ -47,13 +47,16 @@ def _suffix(dtype) -> str:
 def simulate_heston_model(T: float, N: int, R: int, mu: float, kappa: float, v_bar: float, sigma_v: float,
                           rho: float, x0: float, v0: float,
                           numerical_package_bundle: tp.Optional[tp.Type[NumericalPackageBundle]] = B200Bundle,
-                          dtype=np.float32, return_trajectory: bool = False) -> tp.Tuple:
+                          dtype=np.float32, return_trajectory: bool = False,
+                          return_variance_trajectory: bool = False) -> tp.Tuple:
     """Simulate R antithetic Heston paths over N time points (N-1 Euler-Maruyama steps).
 
     Returns device arrays (x_T, v_T), each of shape (R,): path i < ceil(R/2) and path
     i + ceil(R/2) are antithetic partners (the reference's layout, random.py:199-214).
     With ``return_trajectory`` a third array of shape (N, 2*ceil(R/2)) holds every
-    path's log price at every time point (row 0 = x0; the last column of an odd R is unused).
+    path's log price at every time point (row 0 = x0; the last column of an odd R is unused); with
+    ``return_variance_trajectory`` a fourth array of the same shape holds the variances (row 0 = v0) --
+    the path-materialising mode, 8 bytes per path-step written with TMA bulk stores.
     """
     _require_b200(numerical_package_bundle)
     R, N = int(R), int(N)
@@ -65,14 +68,22 @@ def simulate_heston_model(T: float, N: int, R: int, mu: float, kappa: float, v_b
     # shard layout [pairs | partners]: one contiguous buffer, the first R entries are the reference layout
     x = empty_on(ctx, (2 * pairs,), dtype)
     v = empty_on(ctx, (2 * pairs,), dtype)
+    return_trajectory = return_trajectory or return_variance_trajectory
     traj = empty_on(ctx, (N, 2 * pairs), dtype) if return_trajectory else None
+    traj_v = empty_on(ctx, (N, 2 * pairs), dtype) if return_variance_trajectory else None
     p = _params(T, mu, kappa, v_bar, sigma_v, rho, x0, v0)
     k_arr, nK = _lib.strikes_array([1.0])
-    launch = getattr(_lib.lib(), f"cb_heston_price_launch_{sfx}")
-    _lib.check(launch(ctx.handle, ctypes.byref(p), R, N, k_arr, nK, _random.get_seed(), _random.next_subsequence(),
-                      0, pairs, None, x.data_ptr, v.data_ptr, traj.data_ptr if traj is not None else None))
-    out = (x[:R], v[:R])
-    return out + (traj,) if return_trajectory else out
+    seed, sub = _random.get_seed(), _random.next_subsequence()
+    if traj is None:
+        launch = getattr(_lib.lib(), f"cb_heston_price_launch_{sfx}")
+        _lib.check(launch(ctx.handle, ctypes.byref(p), R, N, k_arr, nK, seed, sub, 0, pairs, None, x.data_ptr,
+                          v.data_ptr, None))
+        return x[:R], v[:R]
+    launch = getattr(_lib.lib(), f"cb_heston_trajectory_launch_{sfx}")
+    _lib.check(launch(ctx.handle, ctypes.byref(p), R, N, k_arr, nK, seed, sub, 0, pairs, None, x.data_ptr, v.data_ptr,
+                      traj.data_ptr, traj_v.data_ptr if traj_v is not None else None))
+    out = (x[:R], v[:R], traj)
+    return out + (traj_v,) if traj_v is not None else out
 
 
 def call_payoff_sums(x_simulated: ndarray, strikes: tp.Sequence[float]) -> tp.Tuple[np.ndarray, np.ndarray]:

@@ -196,6 +196,21 @@ CB_API int cb_heston_payoff_launch_f64(cb_ctx *ctx, const cb_heston_params *p, u
                                        const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
                                        uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
                                        const cb_payoff_spec *spec);
+/* Path-materialising mode with both state variables (the HBM-write-bound variant, 8 bytes per path-step): the
+ * log price x_t of every time point goes to d_traj_x and the variance v_t to d_traj_v (NULL: log prices only, i.e.
+ * cb_heston_price_launch's d_traj), each [N][2*pair_count], row t = time point t (row 0 = x0 / v0), columns
+ * [first halves | partners] of the shard -- the state simulate_heston_model ping-pongs through
+ * (heston_utilities.py:60-64, :85-91), kept instead of overwritten.  The stores are TMA bulk copies from a
+ * shared-memory stage when pair_count*sizeof(real) is a multiple of 16 and the shard holds no unpaired path,
+ * warp-coalesced direct stores otherwise.  d_x/d_v (terminal state) may be NULL; sums as in cb_heston_price_launch. */
+CB_API int cb_heston_trajectory_launch_f32(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                           const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                           uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                                           float *d_x, float *d_v, float *d_traj_x, float *d_traj_v);
+CB_API int cb_heston_trajectory_launch_f64(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
+                                           const double *h_strikes, int nK, uint64_t seed, uint32_t subsequence,
+                                           uint64_t pair_first, uint64_t pair_count, cb_comm *comm,
+                                           double *d_x, double *d_v, double *d_traj_x, double *d_traj_v);
 /* The whole multi-GPU job of simulate_and_compute_option_price_gpu (heston_utilities.py:217-270) in one call:
  * shard g of G owns pairs [g*ceil(P/G), min((g+1)*ceil(P/G), P)), P = ceil(R/2); every context's stream gets its
  * kernel followed by the one ncclAllReduce (grouped); the reduced sums are read once from ctxs[0].  comms may be
@@ -264,7 +279,9 @@ CB_API int cb_group_end(void);
  *       7 Philox4x32-10 calls, 8 HBM write (bytes), 9 LOP3 (ALU pipe),
  *       10 HBM copy (read+write bytes), 11-17 integer-multiply issue-cost experiments
  *       (IMAD.WIDE alone / with FFMA / with LOP3, IMAD.HI, IMAD lo),
- *       18-20 packed FFMA2 (fma.rn.f32x2) alone / with FFMA / with LOP3
+ *       18-20 packed FFMA2 (fma.rn.f32x2) alone / with FFMA / with LOP3,
+ *       21-38 pipe-model probes: mixes of half Philox rounds (IMAD.WIDE + XOR), three-register FFMA, LOP3 and
+ *       FADD on independent chains (csrc/peaks.cu: peak_mix_kernel)
  * ops_per_s: thread-level operations per second (FFMA counts 1 op = 2 flop). */
 CB_API int cb_peak_measure(cb_ctx *ctx, int kind, int repeats, double *ops_per_s, float *ms_best);
 

@@ -1,0 +1,96 @@
+"""TEST / BENCH INFRASTRUCTURE ONLY -- never imported by the product (cocos_b200/).
+
+Stages the UNMODIFIED reference (michaelnowotny/cocos) from /root/reference into
+``oracle/_ref/`` so that it travels to the GPU box with the snapshot (``oracle/_ref/``
+is git-ignored -- nothing of the reference enters the history -- but not
+gpurun-ignored, like the built ``.so`` files).  ``bench.py --impl reference`` and the
+``cpu_baseline`` leg then time the reference's own ``simulate_and_compute_option_price``
+(examples/stochastic_volatility/heston_utilities.py:122-164) on its NumPy bundle,
+imported from ``oracle/_ref`` under the stubs of ``oracle/reference_runner.py``.
+
+What is staged: the ``cocos`` package (pure Python, 0.6 MB) and the ``examples`` tree
+(the Heston and pi examples live there, outside the installable package -- which is
+why ``pip install --target`` alone would not do).  Tests, notebooks and images are
+not staged.  A manifest with the SHA-256 of every staged file is written next to
+them; ``verify()`` recomputes it, so a staged copy that was edited is detected.
+
+    python oracle/build_ref.py            # stage (idempotent)
+    python oracle/build_ref.py --verify   # check the staged copy against its manifest
+"""
+import hashlib
+import json
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCE_ROOT = "/root/reference"
+STAGED_ROOT = os.path.join(HERE, "_ref")
+MANIFEST = os.path.join(STAGED_ROOT, "MANIFEST.json")
+_TREES = ("cocos", "examples")
+_SKIP_DIRS = {"tests", "__pycache__"}
+
+
+def _sha256(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as fh:
+        for chunk in iter(lambda: fh.read(1 << 16), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def _python_files(root):
+    for tree in _TREES:
+        for base, dirs, files in os.walk(os.path.join(root, tree)):
+            dirs[:] = sorted(d for d in dirs if d not in _SKIP_DIRS)
+            for name in sorted(files):
+                if name.endswith(".py"):
+                    yield os.path.relpath(os.path.join(base, name), root)
+
+
+def source_available():
+    return os.path.isdir(os.path.join(SOURCE_ROOT, "cocos"))
+
+
+def staged_available():
+    return os.path.isfile(MANIFEST) and os.path.isdir(os.path.join(STAGED_ROOT, "cocos"))
+
+
+def stage(verbose=True):
+    """Copy the reference's Python files, byte for byte, into oracle/_ref/ and write the manifest."""
+    if not source_available():
+        if verbose:
+            print(f"build_ref: {SOURCE_ROOT} is not mounted; keeping whatever is staged "
+                  f"({'present' if staged_available() else 'nothing'})")
+        return staged_available()
+    manifest = {}
+    for rel in _python_files(SOURCE_ROOT):
+        src, dst = os.path.join(SOURCE_ROOT, rel), os.path.join(STAGED_ROOT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        digest = _sha256(src)
+        if not (os.path.exists(dst) and _sha256(dst) == digest):
+            shutil.copyfile(src, dst)
+        manifest[rel] = digest
+    with open(MANIFEST, "w") as fh:
+        json.dump({"source": SOURCE_ROOT, "files": manifest}, fh, indent=1, sort_keys=True)
+    if verbose:
+        print(f"build_ref: staged {len(manifest)} reference files under {STAGED_ROOT}")
+    return True
+
+
+def verify():
+    """True when every staged file still has the digest recorded at staging time (i.e. is unmodified)."""
+    if not staged_available():
+        return False
+    with open(MANIFEST) as fh:
+        files = json.load(fh)["files"]
+    return all(os.path.exists(os.path.join(STAGED_ROOT, rel)) and _sha256(os.path.join(STAGED_ROOT, rel)) == digest
+               for rel, digest in files.items())
+
+
+if __name__ == "__main__":
+    if "--verify" in sys.argv:
+        ok = verify()
+        print("build_ref: staged copy", "matches its manifest" if ok else "is missing or modified")
+        sys.exit(0 if ok else 1)
+    sys.exit(0 if stage() else 1)

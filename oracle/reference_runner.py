@@ -8,15 +8,18 @@ branch never touches ArrayFire, but the modules import it at the top
 (cocos/numerics/random.py:1, cocos/device.py:1) and use ``af.broadcast`` as an
 import-time decorator (cocos/numerics/_array.py:321).  We therefore put inert
 stand-ins for the missing third-party modules into ``sys.modules`` before
-importing the reference.  Nothing of the reference is copied: it is imported
-from where it lies.  This file only works in the build container (the GPU box
-has no /root/reference); tests use the fixtures it wrote to tests/golden/.
+importing the reference.  The reference is imported from where it lies (/root/reference in the build
+container) or, on the GPU box, from the byte-for-byte staged copy under
+``oracle/_ref/`` (git-ignored, written by oracle/build_ref.py; bench.py's CPU arm
+is its only user there).  Tests use the fixtures this file wrote to tests/golden/.
 """
+import os
 import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = "/root/reference"
+_STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_ROOT = "/root/reference" if os.path.isdir("/root/reference/cocos") else _STAGED_ROOT
 
 _STUBBED = (
     "arrayfire", "arrayfire.library", "arrayfire.arith", "arrayfire.array",
@@ -27,8 +30,8 @@ _STUBBED = (
 
 
 def reference_available() -> bool:
-    import os
-    return os.path.isdir(REFERENCE_ROOT + "/cocos")
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "cocos")) and \
+        os.path.isfile(os.path.join(REFERENCE_ROOT, "examples", "stochastic_volatility", "heston_utilities.py"))
 
 
 def install_stubs() -> None:
@@ -46,7 +49,7 @@ def install_stubs() -> None:
 def load_reference() -> types.SimpleNamespace:
     """Import the reference's hot-path callables (NumPy branch)."""
     if not reference_available():
-        raise RuntimeError("reference tree not mounted at " + REFERENCE_ROOT)
+        raise RuntimeError("reference tree neither mounted at /root/reference nor staged under " + _STAGED_ROOT)
     install_stubs()
     from cocos.numerics.random import (            # noqa: E402
         randn_antithetic, rand_antithetic, get_antithetic_slices)
@@ -107,3 +110,36 @@ class InjectedNormals:
         import numpy
         numpy.random.randn, numpy.random.rand = self._saved
         return False
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's CPU multi-core pricing (heston_utilities.py:167-214): map_reduce_multicore over
+# number_of_cores = 5 * cpu_count() equal batches of ceil(R / number_of_cores) paths, the batch prices folded as
+# x + y / number_of_cores.  loky/pathos (the reference's process pools) are absent from this image, so the batches
+# are dispatched with concurrent.futures; every batch runs the reference's own, unmodified
+# simulate_and_compute_option_price on its NumpyBundle.
+
+_REF = None
+
+
+def reference_batch_price(args):
+    """Worker: one batch of the unmodified reference entry point (NumPy bundle), seeded per batch."""
+    global _REF
+    seed, kwargs = args
+    if _REF is None:
+        _REF = load_reference()
+    import numpy
+    numpy.random.seed(seed)
+    return _REF.simulate_and_compute_option_price(numerical_package_bundle=_REF.NumpyBundle, **kwargs)
+
+
+def reference_multicore_price(executor, R, number_of_batches, seed0, **kwargs):
+    """simulate_and_compute_option_price_multicore semantics on a concurrent.futures executor.
+    Returns (price, paths actually simulated = number_of_batches * ceil(R / number_of_batches))."""
+    import math
+    per_batch = math.ceil(R / number_of_batches)
+    jobs = [(seed0 + i, dict(kwargs, R=per_batch)) for i in range(number_of_batches)]
+    price = 0.0
+    for p in executor.map(reference_batch_price, jobs):        # ordered: the reference folds in list order
+        price = price + p / number_of_batches
+    return price, per_batch * number_of_batches

@@ -39,22 +39,30 @@ def injected_host(ctx, Z, R, N, p):
 
 
 def fused(ctx, p, R, N, strikes, seed, sub, first=0, count=None, dtype=np.float32, outputs=False, traj=False,
-          comm=None):
-    """cb_heston_price_launch + finish -> (sums, sumsq[, x, v[, traj]]) as numpy."""
+          comm=None, traj_v=False):
+    """cb_heston_price_launch (cb_heston_trajectory_launch with traj_v) + finish -> (sums, sumsq[, x, v[, traj[, traj_v]]])
+    as numpy."""
     sfx = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}[np.dtype(dtype)]
     H = (R + 1) // 2
     count = H - first if count is None else count
     k_arr, nK = _lib.strikes_array(strikes)
     hp = hparams(p)
-    dx = dv = dt = None
+    dx = dv = dt = dtv = None
+    traj = traj or traj_v
     if outputs or traj:
         dx, dv = empty_on(ctx, (2 * max(count, 1),), dtype), empty_on(ctx, (2 * max(count, 1),), dtype)
     if traj:
         dt = empty_on(ctx, (N, 2 * max(count, 1)), dtype)
-    fn = getattr(_lib.lib(), f"cb_heston_price_launch_{sfx}")
-    _lib.check(fn(ctx.handle, ctypes.byref(hp), R, N, k_arr, nK, seed, sub, first, count, comm,
-                  dx.data_ptr if dx is not None else None, dv.data_ptr if dv is not None else None,
-                  dt.data_ptr if dt is not None else None))
+    if traj_v:
+        dtv = empty_on(ctx, (N, 2 * max(count, 1)), dtype)
+        fn = getattr(_lib.lib(), f"cb_heston_trajectory_launch_{sfx}")
+        _lib.check(fn(ctx.handle, ctypes.byref(hp), R, N, k_arr, nK, seed, sub, first, count, comm, dx.data_ptr,
+                      dv.data_ptr, dt.data_ptr, dtv.data_ptr))
+    else:
+        fn = getattr(_lib.lib(), f"cb_heston_price_launch_{sfx}")
+        _lib.check(fn(ctx.handle, ctypes.byref(hp), R, N, k_arr, nK, seed, sub, first, count, comm,
+                      dx.data_ptr if dx is not None else None, dv.data_ptr if dv is not None else None,
+                      dt.data_ptr if dt is not None else None))
     sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
     _lib.check(_lib.lib().cb_heston_price_finish(ctx.handle, nK, sums, sumsq))
     out = [np.array(sums), np.array(sumsq)]
@@ -62,6 +70,8 @@ def fused(ctx, p, R, N, strikes, seed, sub, first=0, count=None, dtype=np.float3
         out += [dx.to_numpy(), dv.to_numpy()]
     if dt is not None:
         out.append(dt.to_numpy())
+    if dtv is not None:
+        out.append(dtv.to_numpy())
     return out
 
 

@@ -41,8 +41,9 @@ def main():
         ops, ms = ctypes.c_double(0), ctypes.c_float(0)
         _lib.check(L.cb_peak_measure(ctx.handle, kind, 3, ctypes.byref(ops), ctypes.byref(ms)))
         return ops.value
-    hbm_w, hbm_c, dfma = peak(8), peak(10), peak(6)
-    res["peaks"] = {"hbm_write_GBs": hbm_w / 1e9, "hbm_copy_GBs": hbm_c / 1e9, "dfma_per_s": dfma}
+    hbm_w, hbm_c, dfma, philox = peak(8), peak(10), peak(6), peak(7)
+    res["peaks"] = {"hbm_write_GBs": hbm_w / 1e9, "hbm_copy_GBs": hbm_c / 1e9, "dfma_per_s": dfma,
+                    "philox_calls_per_s": philox}
 
     # ---- random arrays (HBM-write bound)
     n = 1 << 30
@@ -93,6 +94,28 @@ def main():
                                              "frac_hbm_write": byts / ms / 1e6 / (hbm_w / 1e9)}
         del x, v, traj
 
+    # ---- (x, v) path-materialising mode: 8 B written per path-step (the HBM-bound variant of SURVEY section 8d)
+    for Rr, N in ((4_000_000, 101), (2_000_000, 253)):
+        pairs = Rr // 2
+        x, v = empty_on(ctx, (Rr,), np.float32), empty_on(ctx, (Rr,), np.float32)
+        tx, tv = empty_on(ctx, (N, Rr), np.float32), empty_on(ctx, (N, Rr), np.float32)
+        k_arr, nK = _lib.strikes_array([0.95])
+
+        def go_xv():
+            _lib.check(L.cb_heston_trajectory_launch_f32(ctx.handle, ctypes.byref(HP), Rr, N, k_arr, nK, 0, 5, 0, pairs,
+                                                         None, x.data_ptr, v.data_ptr, tx.data_ptr, tv.data_ptr))
+        ms = timed(ctx, go_xv)
+        byts = 2 * N * Rr * 4
+        res[f"trajectory_xv_f32_R{Rr}_N{N}"] = {"ms": ms, "path_steps_per_s": Rr * (N - 1) / ms * 1e3,
+                                                "GBs_written": byts / ms / 1e6,
+                                                "frac_hbm_write": byts / ms / 1e6 / (hbm_w / 1e9)}
+        os.environ["COCOS_B200_NO_BULK"] = "1"
+        ms = timed(ctx, go_xv)
+        del os.environ["COCOS_B200_NO_BULK"]
+        res[f"trajectory_xv_f32_R{Rr}_N{N}_direct_stores"] = {"ms": ms, "GBs_written": byts / ms / 1e6,
+                                                              "frac_hbm_write": byts / ms / 1e6 / (hbm_w / 1e9)}
+        del x, v, tx, tv
+
     # ---- fused variants: strike sweeps and float64 state (C5 shape per GPU: 12.5M paths x 252 steps, 64 strikes)
     strikes64 = [0.70 + 0.60 * i / 63 for i in range(64)]
     for name, sfx, Rr, N, ks in (("fused_f32_1strike_C3", "f32", 10_000_000, 501, [0.95]),
@@ -119,7 +142,10 @@ def main():
         ms = timed(ctx, go)
         inside = ctypes.c_uint64(0)
         _lib.check(L.cb_pi_count_finish(ctx.handle, ctypes.byref(inside)))
-        res[f"pi_1e9_{'antithetic' if anti else 'plain'}"] = {"ms": ms, "points_per_s": nn / ms * 1e3, "pi": 4 * inside.value / nn}
+        calls = ndraw / 2                      # one Philox4x32-10 block feeds two draws
+        res[f"pi_1e9_{'antithetic' if anti else 'plain'}"] = {"ms": ms, "points_per_s": nn / ms * 1e3, "pi": 4 * inside.value / nn,
+                                                              "philox_calls_per_s": calls / ms * 1e3,
+                                                              "frac_philox_call_peak": calls / ms * 1e3 / philox}
 
     # ---- derived distributions (one fused kernel each) and the Gaussian KDE (MUFU.EX2 per pair)
     mufu = min(peak(4), peak(1))
@@ -137,7 +163,7 @@ def main():
     x, _ = heston.simulate_heston_model(T=P["T"], N=101, R=2_000_000, mu=P["r"], kappa=P["kappa"], v_bar=P["v_bar"],
                                         sigma_v=P["sigma_v"], rho=P["rho"], x0=P["x0"], v0=P["v0"])
     ctx.sync()
-    prices = dev_array(x.tensor.exp(), ctx)
+    prices = np.exp(x.to_numpy())
     kde = gaussian_kde(prices)
     for m in (1000, 100_000):
         grid = np.linspace(0.3, 2.0, m)
