@@ -113,4 +113,5 @@ __device__ __forceinline__ void euler_pair(real &x1, real &u1, real &x2, real &u
     u2 = floor_min(fma(q2, -g, fma(u2, k.decay, k.pull_u)), k.floor_u);
 }
 
+
 }  // namespace cb

@@ -230,7 +230,7 @@ cudaError_t trajectory_occupancy(bool with_v, bool multi, bool bulk, int *thread
     const void *fn = trajectory_fn<real>(with_v, multi, bulk);
     const size_t smem = trajectory_smem_bytes<real>(with_v, bulk);
     *threads = kTrajThreads;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // static shared memory (strikes, reduction scratch) comes on top of the stage
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -243,7 +243,7 @@ cudaError_t launch_heston_trajectory(const FusedConsts<real> &c, int blocks, boo
     const bool with_v = d_traj_v != nullptr;
     const void *fn = trajectory_fn<real>(with_v, c.nK > 1, bulk);
     const size_t smem = trajectory_smem_bytes<real>(with_v, bulk);
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {   // static shared memory (strikes, reduction scratch) comes on top of the stage
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }

@@ -15,7 +15,9 @@
 //     a uniform high word); two Philox calls per trip give the scheduler independent chains;
 //   * the interior of the range (both draws of a block owned and reflected) runs branch-free; the at most two
 //     ragged blocks at the ends of a shard are counted by one thread with the plain code;
-//   * the inside test is a predicate and a predicated add -- ALU-pipe work beside the FMA pipe's multiplies.
+//   * the inside test is ONE saturating FMA that yields 1.0 or 0.0 (inside_indicator) and the count is kept in a
+//     float (exact below 2^24, flushed to the 64-bit counter in bursts): full-rate FMA-pipe work instead of a
+//     compare and a predicated add on the half-rate ALU pipe (profiles/r02_pipe_model.md).
 // Grid = every resident block the device can hold (occupancy query), not a fixed blocks-per-SM guess.
 // The last block to finish (atomic ticket) owns the total; with a communicator that has NVLink peer mappings it
 // also runs the cross-GPU sum there (peer_exchange_fold), so no collective follows the kernel.
@@ -28,18 +30,28 @@ __device__ __forceinline__ unsigned inside(float x, float y) {
     return __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)) <= 1.0f ? 1u : 0u;
 }
 
-// points inside among the two draws of one block and (ANTI) their reflections
+// 1.0f when rn(rn(x*x) + rn(y*y)) <= 1, else 0.0f -- on the FMA pipe: s takes the values ..., 1-2^-24, 1, 1+2^-23, ...
+// around the threshold, and 2^23*(1-s) + 1 (exact in an FMA) is >= 1 for s <= 1 and <= 0 for s >= 1+2^-23, so the
+// saturating FMA is the indicator.  A compare + predicated add would be two ALU-pipe instructions at half rate.
+__device__ __forceinline__ float inside_indicator(float x, float y) {
+    const float s = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, 0fCB000000, 0f4B000001;" : "=f"(r) : "f"(s));   // sat(s * -2^23 + (2^23 + 1))
+    return r;
+}
+
+// points inside among the two draws of one block and (ANTI) their reflections (exact small integers in float)
 template <bool ANTI>
-__device__ __forceinline__ void block_count(const uint4 &o, uint32_t &cnt) {
+__device__ __forceinline__ float block_count(const uint4 &o) {
     const float mx0 = mantissa_float(o.x), my0 = mantissa_float(o.y);
     const float mx1 = mantissa_float(o.z), my1 = mantissa_float(o.w);
-    // one predicated add per point (FSETP + @P IADD): both on the ALU pipe, next to the FMA pipe's Philox multiplies
-    if (__fadd_rn(__fmul_rn(__fadd_rn(mx0, -1.0f), __fadd_rn(mx0, -1.0f)), __fmul_rn(__fadd_rn(my0, -1.0f), __fadd_rn(my0, -1.0f))) <= 1.0f) ++cnt;
-    if (__fadd_rn(__fmul_rn(__fadd_rn(mx1, -1.0f), __fadd_rn(mx1, -1.0f)), __fmul_rn(__fadd_rn(my1, -1.0f), __fadd_rn(my1, -1.0f))) <= 1.0f) ++cnt;
+    float c = inside_indicator(__fadd_rn(mx0, -1.0f), __fadd_rn(my0, -1.0f)) +
+              inside_indicator(__fadd_rn(mx1, -1.0f), __fadd_rn(my1, -1.0f));
     if constexpr (ANTI) {      // 1 - u = 2 - mantissa_float, exact like u itself
-        if (__fadd_rn(__fmul_rn(__fsub_rn(2.0f, mx0), __fsub_rn(2.0f, mx0)), __fmul_rn(__fsub_rn(2.0f, my0), __fsub_rn(2.0f, my0))) <= 1.0f) ++cnt;
-        if (__fadd_rn(__fmul_rn(__fsub_rn(2.0f, mx1), __fsub_rn(2.0f, mx1)), __fmul_rn(__fsub_rn(2.0f, my1), __fsub_rn(2.0f, my1))) <= 1.0f) ++cnt;
+        c += inside_indicator(__fsub_rn(2.0f, mx0), __fsub_rn(2.0f, my0)) +
+             inside_indicator(__fsub_rn(2.0f, mx1), __fsub_rn(2.0f, my1));
     }
+    return c;
 }
 
 template <bool ANTI>
@@ -63,7 +75,6 @@ pi_count_kernel(uint64_t n, uint64_t draw_first, uint64_t draw_count, const __gr
 
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t cnt = 0;                          // points inside, per segment and thread
     unsigned long long count = 0;
     // segments of the block index with a uniform high word (one segment unless n exceeds 2^34 points)
     for (uint64_t seg = in_first; seg < in_end;) {
@@ -76,16 +87,21 @@ pi_count_kernel(uint64_t n, uint64_t draw_first, uint64_t draw_count, const __gr
         // every thread takes blocks lo_first + gtid + i*stride, two per trip; 32-bit arithmetic inside the loop
         const uint64_t mine = span > gtid ? (span - gtid + stride - 1) / stride : 0;
         uint32_t c0 = lo_first + gtid;
-        for (uint32_t t = (uint32_t)(mine >> 1); t > 0; --t) {
-            const uint4 a = tail.call(c0, k);
-            const uint4 b = tail.call(c0 + stride, k);
-            c0 += 2u * stride;
-            block_count<ANTI>(a, cnt);
-            block_count<ANTI>(b, cnt);
+        // float accumulators hold exact counts below 2^24: 8 points per trip, flushed every 2^20 trips
+        uint32_t left = (uint32_t)(mine >> 1);
+        while (left > 0) {
+            const uint32_t burst = left < (1u << 20) ? left : (1u << 20);
+            float acc = 0.0f;
+            for (uint32_t t = burst; t > 0; --t) {
+                const uint4 a = tail.call(c0, k);
+                const uint4 b = tail.call(c0 + stride, k);
+                c0 += 2u * stride;
+                acc += block_count<ANTI>(a) + block_count<ANTI>(b);
+            }
+            count += (unsigned long long)acc;
+            left -= burst;
         }
-        if (mine & 1) block_count<ANTI>(tail.call(c0, k), cnt);
-        count += cnt;                                           // per segment and thread < 2^32 points
-        cnt = 0;
+        if (mine & 1) count += (unsigned long long)block_count<ANTI>(tail.call(c0, k));
         seg = seg_end;
     }
     // ragged blocks at the ends of the shard: a draw not owned, or the unreflected last draw of an odd n
