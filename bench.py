@@ -6,16 +6,30 @@ A "step" is one pricing pass: R antithetic Heston paths x (nT-1) Euler steps red
 a discounted call price.  Workload at N=1: BASELINE config C3 (10M paths x 500 steps,
 float32, fused in-kernel Philox).  For N>1 (launched by torchrun, one rank per GPU) the
 per-GPU work is fixed (weak scaling): the job simulates N x 10M paths, sharded by
-antithetic pair range, and one NCCL allreduce per step combines the payoff sums.
+antithetic pair range, and the cross-GPU sum of the payoff totals runs inside the kernel
+over NVLink peer memory (one NCCL allreduce per step where peer mappings are unavailable).
 
 Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the kernel's
 stream, max over ranks) with everything resident; `e2e` is the same metric through the
 public Python entry point (host scalars in, host float out, wall clock around it);
 `roofline` is against the MUFU (SFU) pipe peak measured live by a calibration kernel;
-`cpu_baseline` / `--impl reference` time the NumPy restatement of the reference's CPU
-path (oracle/, test infrastructure -- the reference tree itself is not on the GPU box).
+`cpu_baseline` / `--impl reference` time the reference's OWN, unmodified
+`simulate_and_compute_option_price` on its NumPy bundle (staged byte for byte under
+oracle/_ref by oracle/build_ref.py, run under the import stubs of oracle/reference_runner.py)
+with the batching of its multicore entry point: 5 x cpu_count() batches over all host
+cores, the full 10M paths per step.
+
+After the timed regions, `extras` carries what the headline line cannot (untimed for the
+headline, each entry device-timed on its own): every other BASELINE config that fits the
+job -- C1 (injected normals, bit-compared with the C oracle), C2 (pi, 1e9 antithetic
+points, count bit-compared with the oracle at a reduced n), the path-materialising mode
+(x only and x,v) at N=1; C4 (1B x 1000, sharded over the N GPUs) at N>=2 and C5 (100M x
+252 float64, 64 strikes) at N=8 -- and at N>1 the device-count invariance of the sharded
+sum: fused exchange == NCCL allreduce == sum of the ranks' shard sums == the 1-GPU value
+stored in tests/golden/fused_c3_sums.json.
 """
 import argparse
+import ctypes
 import json
 import math
 import os
@@ -36,42 +50,64 @@ METRIC = "heston_mc_path_steps_per_sec"
 UNIT = "path-steps/s"
 # algorithmic work per path-step: 24 FP32 flop, 3 SFU ops, 25 INT ops, 0 DRAM bytes
 FLOP_PER_PATH_STEP, SFU_PER_PATH_STEP = 24, 3
+GOLDEN_SUMS = os.path.join(ROOT, "tests", "golden", "fused_c3_sums.json")
+STRIKES64 = [0.70 + 0.60 * i / 63 for i in range(64)]
 
 
-# --------------------------------------------------------------------------- CPU arm
+# --------------------------------------------------------------------------- CPU arm (the reference itself)
 
-def _cpu_batch(args):
-    """One batch of the reference's NumPy path (restated in oracle/heston_numpy.py)."""
+class CpuArm:
+    """The reference's CPU multi-core pricing (heston_utilities.py:167-214) on all host cores: 5 x cpu_count()
+    equal batches through the UNMODIFIED simulate_and_compute_option_price(NumpyBundle); falls back to the NumPy
+    restatement (kind "port") only when the staged reference is absent."""
+
+    def __init__(self, nT=N_T):
+        from concurrent.futures import ProcessPoolExecutor
+        import multiprocessing
+        from oracle import reference_runner as rr
+        self.cores = os.cpu_count() or 1
+        self.nT = nT
+        self.kind = "reference" if rr.reference_available() else "port"
+        self.batches = 5 * self.cores                       # heston_utilities.py:181-183
+        # one BLAS/OpenMP thread per worker process, as loky -- the reference's default process pool
+        # (cocos/multi_processing/utilities.py, MultiprocessingPoolType.LOKY) -- arranges for its workers
+        # (max(cpu_count // n_workers, 1)); without it cores x cores OpenBLAS threads fight over the cores
+        for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = "1"
+        self.pool = ProcessPoolExecutor(max_workers=self.cores, mp_context=multiprocessing.get_context("spawn"))
+        self.kwargs = dict(PARAMS, nT=nT)
+        # start the workers and import the reference in each of them (untimed, like the reference's own warm-up call,
+        # heston_pricing_benchmark.py:105-118)
+        self.step(2_000 * self.batches, seed0=9_000_000)
+
+    def step(self, R, seed0=0):
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            from oracle import reference_runner as rr
+            price, paths = rr.reference_multicore_price(self.pool, R, self.batches, seed0, **self.kwargs)
+        else:
+            per = math.ceil(R / self.batches)
+            prices = list(self.pool.map(_port_batch, [(seed0 + i, per, self.nT) for i in range(self.batches)]))
+            price, paths = sum(prices) / len(prices), per * self.batches
+        dt = time.perf_counter() - t0
+        return paths * (self.nT - 1) / dt, dt, price, paths
+
+    def describe(self, paths):
+        what = ("the reference's unmodified simulate_and_compute_option_price on its NumpyBundle (staged copy, "
+                "import stubs for arrayfire)" if self.kind == "reference" else "NumPy restatement of the reference path")
+        return (f"{self.batches} batches (5 x cpu_count) of {paths // self.batches} paths x {self.nT - 1} steps = "
+                f"{paths} paths per step, {what}, {self.cores} worker processes")
+
+    def close(self):
+        self.pool.shutdown()
+
+
+def _port_batch(args):
     seed, R, nT = args
     import numpy as np
     from oracle import heston_numpy as hn
     np.random.seed(seed)
     return hn.price(nT=nT, R=R, **PARAMS)
-
-
-class CpuArm:
-    """map_reduce_multicore semantics (multi_core_batch_processing.py:10-94) over all host cores."""
-
-    def __init__(self, batch_paths=100_000, nT=N_T):
-        from concurrent.futures import ProcessPoolExecutor
-        import multiprocessing
-        self.cores = os.cpu_count() or 1
-        self.batch_paths, self.nT = batch_paths, nT
-        self.pool = ProcessPoolExecutor(max_workers=self.cores, mp_context=multiprocessing.get_context("spawn"))
-        list(self.pool.map(_cpu_batch, [(i, 1000, 11) for i in range(self.cores)]))     # start the workers
-
-    def step(self, batches, seed0=0):
-        t0 = time.perf_counter()
-        prices = list(self.pool.map(_cpu_batch, [(seed0 + i, self.batch_paths, self.nT) for i in range(batches)]))
-        dt = time.perf_counter() - t0
-        return batches * self.batch_paths * (self.nT - 1) / dt, dt, sum(prices) / len(prices)
-
-    def describe(self, batches):
-        return (f"{batches} batches x {self.batch_paths} paths x {self.nT - 1} steps, NumPy restatement of the "
-                f"reference path in {self.cores} worker processes")
-
-    def close(self):
-        self.pool.shutdown()
 
 
 def cpu_model():
@@ -86,30 +122,46 @@ def cpu_model():
 
 
 def run_reference(args):
+    """The reference arm: the full C3 workload (10M paths x 500 steps) per step on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     arm = CpuArm()
-    batches = max(arm.cores, 8)
-    for w in range(min(args.warmup, 1)):
-        arm.step(batches, seed0=10_000 + w)
+    R = PATHS_PER_GPU
+    warmups = 0
+    budget_s = float(os.environ.get("COCOS_B200_CPU_ARM_BUDGET_S", "280"))
+    t_begin = time.perf_counter()
+    per_step = None
+    for w in range(args.warmup):
+        # a warm-up step costs as much as a timed one (seconds): run them while they fit the time budget
+        if per_step is not None and (time.perf_counter() - t_begin) + per_step * (args.steps + 1) > budget_s:
+            break
+        _, per_step, _, _ = arm.step(R, seed0=10_000_000 + 1000 * w)
+        warmups += 1
     t0 = time.perf_counter()
-    work = 0
+    work, steps_run, price = 0, 0, float("nan")
     for k in range(args.steps):
-        _, _, _ = arm.step(batches, seed0=1000 * (k + 1))
-        work += batches * arm.batch_paths * (arm.nT - 1)
+        if per_step is not None and steps_run >= 1 and (time.perf_counter() - t_begin) + per_step > budget_s:
+            break                                           # honest count below: `steps` reports what was run
+        _, per_step, price, paths = arm.step(R, seed0=1000 * (k + 1))
+        work += paths * (arm.nT - 1)
+        steps_run += 1
     total = time.perf_counter() - t0
     value = work / total
+    paths = work // (arm.nT - 1) // max(steps_run, 1)
     arm.close()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "steps": steps_run, "warmup": warmups, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 * total / max(steps_run, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3 Heston European call, 10M paths x 500 steps fp32 (CPU arm: bounded sample of "
-                               f"{batches * arm.batch_paths} paths per step)",
-                   "paths": batches * arm.batch_paths, "nT": arm.nT, "antithetic": True},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
-                         "sample": arm.describe(batches) + f", {args.steps} steps", "cpu": cpu_model()},
+        "config": {"workload": "C3 Heston European call, 10M paths x 500 steps fp32 (CPU arm: the reference's NumPy "
+                               "path over all host cores, the full 10M paths per step)",
+                   "paths": paths, "nT": arm.nT, "antithetic": True},
+        "price": price,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                         "sample": arm.describe(paths) + f", {steps_run} steps after {warmups} warm-up steps",
+                         "cpu": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -161,8 +213,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel, from the committed ncu --set full
+    summary (profiles/): (bytes, source file) or (None, None)."""
+    import re
+    for name in ("r02_ncu_fused_f32.md", "r01_ncu_fused_f32.md"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            text = open(path).read()
+        except OSError:
+            continue
+        total, found = 0.0, 0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(r"`" + re.escape(key) + r"`\s*\|\s*([0-9.eE+-]+)\s*\|\s*(\w+)", text)
+            if m:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(2), 1.0)
+                total += float(m.group(1)) * scale
+                found += 1
+        if found == 2:
+            return int(total), "profiles/" + name
+    return None, None
+
+
 def run_b200(args):
-    import ctypes
+    import numpy as np
     import torch
     from cocos_b200 import _lib, distributed as cdist, heston
     from cocos_b200.device import ComputeDeviceManager
@@ -175,6 +249,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     ComputeDeviceManager.set_compute_device(local_rank)
     unique_id = None
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -192,10 +267,17 @@ def run_b200(args):
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
         ctx.sync()
+
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals if len(vals) > 1 else vals[0]
+        t = torch.tensor(list(vals), dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = [float(x) for x in t]
+        return out if len(out) > 1 else out[0]
 
     # ---- pipe peaks, measured live (rank-local; rank 0's are reported)
     def peak(kind):
@@ -205,9 +287,10 @@ def run_b200(args):
     mufu_peak = min(peak(k) for k in (1, 2, 3))          # lg2, sqrt, sin: thread-level MUFU ops/s
     ffma_peak = peak(0)
 
-    # ---- device-resident timing: K launches (+ allreduce), CUDA events on the kernel's stream
+    # ---- device-resident timing: K launches (the cross-GPU sum inside), CUDA events on the kernel's stream
     sub = 0
-    for _ in range(max(args.warmup, 3)):
+    warmups = max(args.warmup, 3)
+    for _ in range(warmups):
         nK = pricer.launch(p, R, N_T, [PARAMS["K"]], args.seed, sub)
         sub += 1
     sums, sumsq = pricer.finish(nK)
@@ -253,35 +336,80 @@ def run_b200(args):
     barrier()
     sampler.stop()
     clocks = sampler.summary()
+    dev_ms, e2e_s, cond_ms = max_over_ranks(dev_ms, e2e_s, cond_ms)
 
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([dev_ms, e2e_s, cond_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, cond_ms = float(t[0]), float(t[1]), float(t[2])
+    # ---- the other BASELINE configs and the invariance of the sharded sum (each device-timed on its own)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_values.json")))
+    extras = {"conditional_scheme": {"value": R * (N_T - 1) * 5 / (cond_ms * 1e-3), "unit": UNIT,
+                                     "price": float(cond_price[0]), "price_se": float(cond_se[0]),
+                                     "note": "opt-in scheme='conditional': log price sampled conditionally on "
+                                             "the variance path, same law as the Euler scheme, 5 launches"}}
+    sfu_roof = mufu_peak / SFU_PER_PATH_STEP
+    fp32_roof = 2 * ffma_peak / FLOP_PER_PATH_STEP
+
+    def timed_sharded(Rj, nT, strikes, sfx, reps, sub0):
+        """best-of-`reps` ms (max over ranks) of one sharded pricing pass + its sums"""
+        nKj = pricer.launch(p, Rj, nT, strikes, args.seed, sub0, sfx)         # warm-up
+        pricer.finish(nKj)
+        best = 1e30
+        for rep in range(reps):
+            barrier()
+            ctx.timer_start()
+            nKj = pricer.launch(p, Rj, nT, strikes, args.seed, sub0 + 1 + rep, sfx)
+            best = min(best, max_over_ranks(ctx.timer_stop()))
+        s_, q_ = pricer.finish(nKj)
+        return best, s_, q_
+
+    def config_entry(name, Rj, nT, strikes, sfx, key, reps=2, sub0=5_000_000):
+        ms, s_, q_ = timed_sharded(Rj, nT, strikes, sfx, reps, sub0)
+        pr, se_ = heston._price_from_sums(PARAMS["r"], PARAMS["T"], Rj, s_, q_)
+        ref = golden["statistical"][key]
+        rate = Rj * (nT - 1) / ms * 1e3
+        entry = {"workload": name, "n_gpus": world, "paths": Rj, "steps": nT - 1, "dtype": sfx, "ms": ms,
+                 "path_steps_per_s": rate, "per_gpu_path_steps_per_s": rate / world}
+        if sfx == "f32":
+            entry["frac_sfu_roofline"] = rate / world / sfu_roof
+        if len(strikes) == 1:
+            entry.update(price=float(pr[0]), price_se=float(se_[0]), reference_price=ref["price"], reference_se=ref["se"],
+                         parity=bool(abs(pr[0] - ref["price"]) <= 3 * math.hypot(se_[0], ref["se"])))
+        else:
+            dev = np.abs(pr - np.array(ref["sweep"]))
+            entry.update(price_K0_70=float(pr[0]), price_K1_30=float(pr[-1]), max_abs_dev_vs_reference=float(dev.max()),
+                         parity=bool(np.all(dev <= 3 * np.hypot(se_, 2 * ref["se"]) + 1e-7)))
+        entry["parity_criterion"] = "price(s) within 3 combined standard errors of the reference's NumPy prices (tests/golden)"
+        return entry
+
+    configs = {}
+    if world == 1:
+        configs.update(_extras_single_gpu(ctx, L, p, mufu_peak, peak))
+    else:
+        configs["C4"] = config_entry("C4 Heston 1B paths x 1000 steps f32 antithetic, sharded over the ranks",
+                                     1_000_000_000, 1001, [PARAMS["K"]], "f32", "nT1001", reps=2)
+        if world == 8:
+            configs["C5"] = config_entry("C5 Heston 100M paths x 252 steps f64, 64-strike sweep sharing paths",
+                                         100_000_000, 253, golden["statistical"]["strikes"], "f64", "nT253", reps=3)
+        configs["C3_strong"] = config_entry("C3 Heston 10M paths x 500 steps f32, strong-scaled over the ranks",
+                                            PATHS_PER_GPU, N_T, [PARAMS["K"]], "f32", "nT501", reps=5)
+        configs["C2"] = _pi_sharded(pricer, ctx, barrier, max_over_ranks)
+        extras["invariance"] = _invariance(pricer, cdist, dist, rank, world, local_rank, p, args.seed)
+    extras["configs"] = configs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         arm = CpuArm()
-        batches = 2 * arm.cores
-        v, dt, cpu_price = arm.step(batches, seed0=777)
-        t1 = time.perf_counter()
-        _cpu_batch((778, arm.batch_paths, arm.nT))                       # one batch in this process: 1 core
-        one_core = arm.batch_paths * (arm.nT - 1) / (time.perf_counter() - t1)
-        cpu = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": "port",
-               "sample": arm.describe(batches) + f" ({dt:.1f} s)", "cpu": cpu_model(), "price": cpu_price,
-               "value_1core": one_core}
+        v, dt, cpu_price, paths = arm.step(PATHS_PER_GPU, seed0=777)
+        cpu = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+               "sample": arm.describe(paths) + f", one step ({dt:.1f} s)", "cpu": cpu_model(), "price": cpu_price}
         arm.close()
 
     if rank == 0:
         work = R * (N_T - 1) * args.steps
         value = work / (dev_ms * 1e-3)
         per_gpu = value / world
-        sfu_roof = mufu_peak / SFU_PER_PATH_STEP
-        fp32_roof = 2 * ffma_peak / FLOP_PER_PATH_STEP
+        traffic, traffic_src = profiled_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": warmups, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C3 Heston European call, 10M paths x 500 steps fp32, fused in-kernel Philox"
                                    + (f", x{world} GPUs sharded by antithetic pair range, cross-GPU sum "
@@ -293,7 +421,8 @@ def run_b200(args):
                        "collective": ("none" if world == 1 else
                                       "fused-peer-exchange" if pricer.peer_exchange else "nccl-allreduce"),
                        "l2": "256 MiB memset between timed steps (the kernel itself reads no memory input)",
-                       "launch": {"threads": args.threads, "blocks_per_sm": args.blocks_per_sm, "ppt": args.ppt}},
+                       "launch": {"threads": args.threads or 256, "blocks_per_sm": args.blocks_per_sm or "max resident",
+                                  "pairs_per_thread": args.ppt or 1}},
             "price": float(price[0]), "price_se": float(se[0]),
             "e2e": {"value": work / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ctypes.sizeof(_lib.HestonParams) + 8,
                     "d2h_bytes_per_step": 16, "price": e2e_price,
@@ -302,27 +431,172 @@ def run_b200(args):
             "gpu_launches": args.steps,
             "roofline": {"bound": "sfu", "achieved": per_gpu * SFU_PER_PATH_STEP / 1e9, "peak": mufu_peak / 1e9,
                          "unit": "GSFUop/s per GPU", "frac": per_gpu / sfu_roof,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture
-                         # (profiles/r01_ncu_fused_f32.md): the kernel's algorithmic DRAM traffic is 0 + 16 B of sums
-                         "traffic": 81920,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, read from the committed ncu --set full
+                         # summary (the kernel's algorithmic DRAM traffic is 0 + 16 B of sums)
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MUFU chain kernels (lg2/sqrt/sin, min) timed live on this GPU; "
                                         "MEASURED_PEAKS.json has no SFU/FP32 figure",
                          "kernel": "heston_fused_kernel<float>", "sfu_ops_per_path_step": SFU_PER_PATH_STEP,
                          "fp32_frac": per_gpu / fp32_roof, "fp32_peak_tflops": 2 * ffma_peak / 1e12,
                          "roof_path_steps_per_s": min(sfu_roof, fp32_roof)},
             "clocks": clocks,
-            "extras": {"conditional_scheme": {"value": R * (N_T - 1) * 5 / (cond_ms * 1e-3), "unit": UNIT,
-                                              "price": float(cond_price[0]), "price_se": float(cond_se[0]),
-                                              "note": "opt-in scheme='conditional': log price sampled conditionally on "
-                                                      "the variance path, same law as the Euler scheme, 5 launches"}},
+            "extras": extras,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     pricer.close()
     if world > 1:
-        import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def _extras_single_gpu(ctx, L, p, mufu_peak, peak):
+    """C1, C2 and the path-materialising mode on one GPU (device-timed, best of a few launches)."""
+    import numpy as np
+    from cocos_b200 import _lib
+    from cocos_b200.numerics._array import empty_on
+    out = {}
+    hbm_write = peak(8)
+    philox_peak = peak(7)
+
+    def best_of(fn, reps=5):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            ctx.timer_start()
+            fn()
+            best = min(best, ctx.timer_stop())
+        return best
+
+    # ---- C1: 100k paths x 100 steps, injected normals, reference operation order; bit-compared with the C oracle
+    from oracle import c_oracle
+    R1, N1 = 100_000, 101
+    H1 = R1 // 2
+    Z = np.random.default_rng(20261020).standard_normal((N1 - 1, H1, 2)).astype(np.float32)
+    dZ = empty_on(ctx, Z.shape, np.float32)
+    _lib.check(L.cb_memcpy_h2d(ctx.handle, dZ.data_ptr, Z.ctypes.data, Z.nbytes))
+    dx, dv = empty_on(ctx, (R1,), np.float32), empty_on(ctx, (R1,), np.float32)
+
+    def c1():
+        _lib.check(L.cb_heston_terminal_injected_f32(ctx.handle, dZ.data_ptr, ctypes.byref(p), R1, N1, dx.data_ptr, dv.data_ptr))
+    ms = best_of(c1)
+    xo, vo = c_oracle.heston_injected(Z, R1, N1, PARAMS["T"], PARAMS["r"], PARAMS["kappa"], PARAMS["v_bar"],
+                                      PARAMS["sigma_v"], PARAMS["rho"], PARAMS["x0"], PARAMS["v0"])
+    xg, vg = dx.to_numpy(), dv.to_numpy()
+    rel = float(np.max(np.abs(np.exp(xg.astype(np.float64)) - np.exp(xo.astype(np.float64))) / np.exp(xo.astype(np.float64))))
+    out["C1"] = {"workload": "C1 Heston 100k paths x 100 steps f32, injected normals (parity kernel)", "ms": ms,
+                 "path_steps_per_s": R1 * (N1 - 1) / ms * 1e3, "GBs_read": Z.nbytes / ms / 1e6,
+                 "bit_identical_to_oracle": bool(np.array_equal(xg, xo) and np.array_equal(vg, vo)),
+                 "max_rel_err_in_S_T": rel, "parity": bool(rel <= 1e-6),
+                 "parity_criterion": "per-path terminal prices within 1e-6 relative of the C restatement of the reference "
+                                     "(pinned to the reference's goldens); bit-identical in practice"}
+    del dZ, dx, dv
+
+    # ---- C2: pi from 1e9 antithetic uniform points; the inside count is bit-compared with the oracle at 2e7 points
+    n_small = 20_000_001
+    _lib.check(L.cb_pi_count_launch(ctx.handle, n_small, 3, 11, 1, 0, (n_small + 1) // 2, None))
+    got = ctypes.c_uint64(0)
+    _lib.check(L.cb_pi_count_finish(ctx.handle, ctypes.byref(got)))
+    want = c_oracle.pi_inside(n_small, 3, 11, True)
+    n = 1_000_000_000
+
+    def c2():
+        _lib.check(L.cb_pi_count_launch(ctx.handle, n, 0, 1, 1, 0, (n + 1) // 2, None))
+    ms = best_of(c2)
+    inside = ctypes.c_uint64(0)
+    _lib.check(L.cb_pi_count_finish(ctx.handle, ctypes.byref(inside)))
+    calls = (n + 1) // 2 / 2
+    out["C2"] = {"workload": "C2 Monte-Carlo pi, 1e9 antithetic uniform points, single launch", "ms": ms,
+                 "points_per_s": n / ms * 1e3, "pi": 4 * inside.value / n,
+                 "philox_calls_per_s": calls / ms * 1e3, "frac_philox_call_peak": calls / ms * 1e3 / philox_peak,
+                 "philox_call_peak_per_s": philox_peak,
+                 "count_at_2e7_points": got.value, "oracle_count_at_2e7_points": want, "parity": bool(got.value == want),
+                 "parity_criterion": "inside count bit-exact against the C oracle (explicit float32 roundings) at 20000001 points"}
+
+    # ---- path-materialising mode: every step of x (4 B/path-step) and of x and v (8 B/path-step) written to HBM
+    Rt, Nt = 4_000_000, 101
+    pairs = Rt // 2
+    k_arr, nK = _lib.strikes_array([PARAMS["K"]])
+    x, v = empty_on(ctx, (Rt,), np.float32), empty_on(ctx, (Rt,), np.float32)
+    tx, tv = empty_on(ctx, (Nt, Rt), np.float32), empty_on(ctx, (Nt, Rt), np.float32)
+    traj = {}
+    for label, tvp, bytes_per in (("x", None, 4), ("x_and_v", tv.data_ptr, 8)):
+        def go():
+            _lib.check(L.cb_heston_trajectory_launch_f32(ctx.handle, ctypes.byref(p), Rt, Nt, k_arr, nK, 0, 5, 0, pairs,
+                                                         None, x.data_ptr, v.data_ptr, tx.data_ptr, tvp))
+        ms = best_of(go)
+        byts = Nt * Rt * bytes_per
+        traj[label] = {"ms": ms, "path_steps_per_s": Rt * (Nt - 1) / ms * 1e3, "GBs_written": byts / ms / 1e6,
+                       "frac_hbm_write": byts / ms / 1e6 / (hbm_write / 1e9), "bytes_per_path_step": bytes_per}
+    ctx.sync()
+    last_x = tx[Nt - 1].to_numpy()
+    traj["last_row_equals_x_T"] = bool(np.array_equal(last_x, x.to_numpy()))
+    traj["hbm_write_peak_GBs"] = hbm_write / 1e9
+    traj["workload"] = f"{Rt} paths x {Nt - 1} steps f32, rows [step][path], TMA bulk stores from a shared-memory stage"
+    out["trajectory"] = traj
+    return out
+
+
+def _pi_sharded(pricer, ctx, barrier, max_over_ranks):
+    """C2 sharded over the ranks: draws split by range, the inside count summed across GPUs inside the kernel."""
+    n = 1_000_000_000
+    pricer.pi_inside(n, 0, 1)
+    best, inside = 1e30, 0
+    for rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        inside = pricer.pi_inside(n, 0, 2 + rep)
+        best = min(best, max_over_ranks((time.perf_counter() - t0) * 1e3))
+    return {"workload": "C2 Monte-Carlo pi, 1e9 antithetic points sharded over the ranks (wall clock incl. host read)",
+            "n_gpus": pricer.world_size, "ms": best, "points_per_s": n / best * 1e3, "pi": 4 * inside / n,
+            "parity": bool(abs(4 * inside / n - math.pi) < 5 * 1.7e-5 * 3.1),
+            "parity_criterion": "estimate within 5 standard errors of pi (the bit-exact count check runs at N=1)"}
+
+
+def _invariance(pricer, cdist, dist, rank, world, local_rank, p, seed):
+    """Device-count invariance of the sharded sum at fixed R = 10M: fused exchange, NCCL allreduce and the plain sum
+    of the ranks' shard sums must agree to 1e-12 relative, and with the 1-GPU value in tests/golden."""
+    import torch
+    Rj, nT, sub = PATHS_PER_GPU, N_T, 424242
+    res = {"R": Rj, "nT": nT, "seed": seed, "subsequence": sub, "tolerance_rel": 1e-12}
+    # (a) the communicator as the bench uses it (fused peer exchange when the mappings exist)
+    nK = pricer.launch(p, Rj, nT, [PARAMS["K"]], seed, sub)
+    a_s, a_q = pricer.finish(nK)
+    res["path_a"] = "fused-peer-exchange" if pricer.peer_exchange else "nccl-allreduce"
+    # (b) a second communicator that never maps peers: the one ncclAllReduce behind the kernel
+    uid2 = cdist.broadcast_unique_id()
+    nccl_only = cdist.ShardedPricer(local_rank, rank, world, uid2, peer_exchange=False)
+    nK = nccl_only.launch(p, Rj, nT, [PARAMS["K"]], seed, sub)
+    b_s, b_q = nccl_only.finish(nK)
+    nccl_only.close()
+    # (c) no exchange at all: every rank's own shard sums, gathered and added in rank order on the host
+    nK = pricer.launch(p, Rj, nT, [PARAMS["K"]], seed, sub, local_only=True)
+    l_s, l_q = pricer.finish(nK)
+    mine = torch.tensor([l_s[0], l_q[0]], dtype=torch.float64, device=f"cuda:{local_rank}")
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    c_s = sum(float(t[0]) for t in parts)
+    c_q = sum(float(t[1]) for t in parts)
+
+    def close(u, w):
+        return abs(u - w) <= 1e-12 * abs(w)
+    res.update(sum_fused=float(a_s[0]), sum_nccl=float(b_s[0]), sum_of_shards=c_s,
+               sumsq_fused=float(a_q[0]), sumsq_nccl=float(b_q[0]), sumsq_of_shards=c_q)
+    ok = close(a_s[0], c_s) and close(b_s[0], c_s) and close(a_q[0], c_q) and close(b_q[0], c_q)
+    try:
+        g = json.load(open(GOLDEN_SUMS))
+        same = g["R"] == Rj and g["nT"] == nT and g["seed"] == seed and g["subsequence"] == sub
+        res["golden_1gpu_sum"] = g["sum"] if same else None
+        if same:
+            res["matches_1gpu_golden"] = bool(close(a_s[0], g["sum"]) and close(a_q[0], g["sumsq"]))
+            ok = ok and res["matches_1gpu_golden"]
+    except OSError:
+        res["golden_1gpu_sum"] = None
+    # every rank must have seen the same thing
+    flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["ok"] = bool(float(flag[0]) == 1.0)
+    return res
 
 
 def main():

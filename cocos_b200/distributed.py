@@ -54,6 +54,8 @@ class ShardedPricer:
         self.ctx = _lib.context(device)
         self.comm = None
         self.peer_exchange = False
+        self._group = group
+        self._mapped = False          # exported or imported anything: the two-phase tear-down applies
         if world_size > 1:
             if unique_id is None or len(unique_id) != _lib.UNIQUE_ID_BYTES:
                 raise ValueError("a 128-byte NCCL unique id is required when world_size > 1")
@@ -72,8 +74,7 @@ class ShardedPricer:
         L = _lib.lib()
         buf = ctypes.create_string_buffer(_lib.P2P_HANDLE_BYTES)
         mine = bytes(buf.raw) if L.cb_comm_p2p_export(self.ctx.handle, self.comm, buf) == 0 else None
-        if mine is not None:
-            mine = bytes(buf.raw)
+        self._mapped = mine is not None
         handles = [None] * self.world_size
         dist.all_gather_object(handles, mine, group=group)
         ok = all(h is not None for h in handles) and \
@@ -81,24 +82,43 @@ class ShardedPricer:
         votes = [None] * self.world_size
         dist.all_gather_object(votes, bool(ok), group=group)
         if not all(votes):
+            # some rank could not map its peers: everybody unmaps what it did map NOW, and nobody frees an exported
+            # buffer before all ranks have done so (the same two phases as close())
+            L.cb_comm_p2p_disconnect(self.comm)
+            dist.barrier(group=group)
+            self._mapped = False
             return False
         _lib.check(L.cb_comm_p2p_enable(self.comm, 1))
         return True
 
     def launch(self, params: "_lib.HestonParams", R: int, nT: int, strikes, seed: int, subsequence: int,
-               dtype_suffix: str = "f32", scheme: str = "euler"):
-        """Asynchronous: this rank's shard of the simulation, then the allreduce, on one stream."""
+               dtype_suffix: str = "f32", scheme: str = "euler", local_only: bool = False):
+        """Asynchronous: this rank's shard of the simulation and the cross-rank sum, on one stream.
+        ``local_only``: no exchange at all -- the result buffer keeps this rank's own shard sums."""
         k_arr, nK = _lib.strikes_array(strikes)
         first, count = pair_shard(R, self.world_size, self.rank)
+        comm = None if local_only else self.comm
         if scheme == "conditional":
             _lib.check(_lib.lib().cb_heston_price_conditional_launch_f32(
                 self.ctx.handle, ctypes.byref(params), int(R), int(nT), k_arr, nK, int(seed), int(subsequence), first,
-                count, self.comm, None, None))
+                count, comm, None, None))
             return nK
         fn = getattr(_lib.lib(), f"cb_heston_price_launch_{dtype_suffix}")
         _lib.check(fn(self.ctx.handle, ctypes.byref(params), int(R), int(nT), k_arr, nK, int(seed), int(subsequence),
-                      first, count, self.comm, None, None, None))
+                      first, count, comm, None, None, None))
         return nK
+
+    def pi_inside(self, n: int, seed: int, subsequence: int, antithetic: bool = True) -> int:
+        """This rank's shard of the draws of a Monte-Carlo pi estimate plus the cross-rank sum of the inside count
+        (fused into the kernel over the peer mappings, or one ncclAllReduce); every rank returns the total."""
+        ndraw = (int(n) + 1) // 2 if antithetic else int(n)
+        first, count = shard_range(ndraw, self.world_size, self.rank)
+        L = _lib.lib()
+        _lib.check(L.cb_pi_count_launch(self.ctx.handle, int(n), int(seed), int(subsequence), int(bool(antithetic)),
+                                        first, count, self.comm))
+        inside = ctypes.c_uint64(0)
+        _lib.check(L.cb_pi_count_finish(self.ctx.handle, ctypes.byref(inside)))
+        return inside.value
 
     def finish(self, nK: int):
         sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
@@ -116,14 +136,15 @@ class ShardedPricer:
 
     def close(self):
         if self.comm is not None:
-            if self.peer_exchange:
+            if self.peer_exchange or self._mapped:
                 # two phases: nobody frees its exported buffer while another rank still has it mapped
                 _lib.lib().cb_comm_p2p_disconnect(self.comm)
                 self.peer_exchange = False
+                self._mapped = False
                 try:
                     import torch.distributed as dist
                     if dist.is_available() and dist.is_initialized():
-                        dist.barrier()
+                        dist.barrier(group=self._group)
                 except Exception:       # noqa: BLE001  (the process group may already be gone at interpreter exit)
                     pass
             _lib.lib().cb_comm_destroy(self.comm)

@@ -8,10 +8,12 @@
     launches are reproducible.
 """
 import math
+import os
 
 import numpy as np
 import pytest
 
+from conftest import GOLDEN
 from gpu_util import fused
 
 pytestmark = pytest.mark.gpu
@@ -121,6 +123,30 @@ def test_shards_add_up(ctx, P, R, parts):
             assert np.array_equal(xs[count:count + n_partner], x[H + first:H + first + n_partner])
     np.testing.assert_allclose(tot_s, s, rtol=1e-12)
     np.testing.assert_allclose(tot_q, q, rtol=1e-12)
+
+
+def test_c3_sums_reproduce_the_committed_golden(ctx, golden_values):
+    """The fixed job of the device-count-invariance checks (bench.py extras.invariance): one GPU reproduces the sums
+    in tests/golden/fused_c3_sums.json bit for bit (fixed-order reduction), and the same job cut into 2, 4 and 8
+    contiguous pair shards -- what 2/4/8 GPUs simulate -- adds up to them to float64 summation order."""
+    import json
+    from cocos_b200.multi_processing.utilities import shard_range
+    g = json.load(open(os.path.join(GOLDEN, "fused_c3_sums.json")))
+    q = golden_values["params"]
+    p = dict(T=q["T"], mu=q["r"], kappa=q["kappa"], v_bar=q["v_bar"], sigma_v=q["sigma_v"], rho=q["rho"], x0=q["x0"],
+             v0=q["v0"])
+    R, nT = g["R"], g["nT"]
+    s, sq = fused(ctx, p, R, nT, [g["K"]], seed=g["seed"], sub=g["subsequence"])
+    assert float(s[0]).hex() == g["sum_hex"] and float(sq[0]).hex() == g["sumsq_hex"]
+    H = (R + 1) // 2
+    for parts in (2, 4, 8):
+        tot_s = tot_q = 0.0
+        for r in range(parts):
+            first, count = shard_range(H, parts, r)
+            a, b = fused(ctx, p, R, nT, [g["K"]], seed=g["seed"], sub=g["subsequence"], first=first, count=count)
+            tot_s += a[0]
+            tot_q += b[0]
+        assert abs(tot_s - g["sum"]) <= 1e-12 * g["sum"] and abs(tot_q - g["sumsq"]) <= 1e-12 * g["sumsq"]
 
 
 def test_trajectory_mode(ctx, P):

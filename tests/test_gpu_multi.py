@@ -237,3 +237,105 @@ def test_fused_peer_exchange_equals_nccl_allreduce(gpu_device, ref_params, monke
         for (s1, q1), (s2, q2) in zip(fused, via_nccl):
             np.testing.assert_allclose(s1, s2, rtol=1e-13)
             np.testing.assert_allclose(q1, q2, rtol=1e-13)
+
+
+@needs2
+def test_fused_exchange_detects_diverged_launch_sequences(gpu_device, ref_params):
+    """Ranks whose calls differ do not get a silently wrong sum: the slots' tags (launch number, element count, call
+    signature) are verified by the folding rank, and a mismatch surfaces as an error from cb_heston_price_finish."""
+    import ctypes
+    from cocos_b200 import _lib
+    L = _lib.lib()
+    q = ref_params
+    p = _lib.HestonParams(q["T"], q["r"], q["kappa"], q["v_bar"], q["sigma_v"], q["rho"], q["x0"], q["v0"])
+    ctxs = [_lib.Context(d) for d in range(2)]
+    harr = (ctypes.c_void_p * 2)(*[c.handle for c in ctxs])
+    comms = (ctypes.c_void_p * 2)()
+    _lib.check(L.cb_comm_init_all(2, harr, comms))
+    active = ctypes.c_int(0)
+    _lib.check(L.cb_comm_p2p_active(ctypes.c_void_p(comms[0]), ctypes.byref(active)))
+    if not active.value:
+        for c in comms:
+            L.cb_comm_destroy(ctypes.c_void_p(c))
+        pytest.skip("no peer access between the devices of this box")
+    k_arr, nK = _lib.strikes_array([0.95])
+    R, N = 100_000, 17
+    H = R // 2
+
+    def launch(rank, sub):
+        first = rank * (H // 2)
+        return L.cb_heston_price_launch_f32(ctxs[rank].handle, ctypes.byref(p), R, N, k_arr, nK, 1, sub, first, H // 2,
+                                            ctypes.c_void_p(comms[rank]), None, None, None)
+
+    def finish(rank):
+        s, sq = (ctypes.c_double * 1)(), (ctypes.c_double * 1)()
+        rc = L.cb_heston_price_finish(ctxs[rank].handle, nK, s, sq)
+        return rc, s[0]
+    # matching calls: both ranks agree
+    assert launch(0, 7) == 0 and launch(1, 7) == 0
+    (rc0, s0), (rc1, s1) = finish(0), finish(1)
+    assert rc0 == 0 and rc1 == 0 and s0 == s1 and s0 > 0
+    # the ranks issue DIFFERENT calls under the same launch number (another subsequence): both must fail loudly
+    assert launch(0, 8) == 0 and launch(1, 9) == 0
+    (rc0, _), (rc1, _) = finish(0), finish(1)
+    assert rc0 != 0 and rc1 != 0
+    assert b"another launch" in L.cb_last_error()
+    # and the communicator recovers: the next matching pair of calls is fine again
+    assert launch(0, 10) == 0 and launch(1, 10) == 0
+    (rc0, s0), (rc1, s1) = finish(0), finish(1)
+    assert rc0 == 0 and rc1 == 0 and s0 == s1
+    for c in comms:
+        L.cb_comm_destroy(ctypes.c_void_p(c))
+
+
+@needs2
+def test_trajectory_and_pi_through_the_fused_exchange(gpu_device, ref_params):
+    """Every launch type carries the cross-GPU sum inside the kernel: trajectory output and the pi count give the
+    totals of the one-device run (no NCCL call is made once peer mappings exist)."""
+    import ctypes
+    from cocos_b200 import _lib
+    from cocos_b200.numerics._array import empty_on
+    from oracle import c_oracle
+    L = _lib.lib()
+    q = ref_params
+    p = _lib.HestonParams(q["T"], q["r"], q["kappa"], q["v_bar"], q["sigma_v"], q["rho"], q["x0"], q["v0"])
+    ctxs = [_lib.Context(d) for d in range(2)]
+    harr = (ctypes.c_void_p * 2)(*[c.handle for c in ctxs])
+    comms = (ctypes.c_void_p * 2)()
+    _lib.check(L.cb_comm_init_all(2, harr, comms))
+    k_arr, nK = _lib.strikes_array([0.95, 1.05])
+    R, N = 40_000, 25
+    H = R // 2
+    # one device, whole job
+    tx = empty_on(ctxs[0], (N, 2 * H), np.float32)
+    x, v = empty_on(ctxs[0], (2 * H,), np.float32), empty_on(ctxs[0], (2 * H,), np.float32)
+    _lib.check(L.cb_heston_trajectory_launch_f32(ctxs[0].handle, ctypes.byref(p), R, N, k_arr, nK, 2, 5, 0, H, None,
+                                                 x.data_ptr, v.data_ptr, tx.data_ptr, None))
+    s1, q1 = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+    _lib.check(L.cb_heston_price_finish(ctxs[0].handle, nK, s1, q1))
+    whole = tx.to_numpy()
+    # two devices, half the pairs each, sums exchanged inside the kernels
+    parts = []
+    for r in range(2):
+        t = empty_on(ctxs[r], (N, H), np.float32)
+        xs, vs = empty_on(ctxs[r], (H,), np.float32), empty_on(ctxs[r], (H,), np.float32)
+        _lib.check(L.cb_heston_trajectory_launch_f32(ctxs[r].handle, ctypes.byref(p), R, N, k_arr, nK, 2, 5, r * (H // 2),
+                                                     H // 2, ctypes.c_void_p(comms[r]), xs.data_ptr, vs.data_ptr,
+                                                     t.data_ptr, None))
+        parts.append(t)
+    for r in range(2):
+        s2, q2 = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
+        _lib.check(L.cb_heston_price_finish(ctxs[r].handle, nK, s2, q2))
+        np.testing.assert_allclose(np.array(s2), np.array(s1), rtol=1e-12)
+        np.testing.assert_allclose(np.array(q2), np.array(q1), rtol=1e-12)
+        got = parts[r].to_numpy()
+        lo = r * (H // 2)
+        assert np.array_equal(got[:, :H // 2], whole[:, lo:lo + H // 2])               # first halves of the shard
+        assert np.array_equal(got[:, H // 2:], whole[:, H + lo:H + lo + H // 2])       # their partners
+    # pi: bit-exact count whatever the exchange path
+    n = 30_000_001
+    inside = ctypes.c_uint64(0)
+    _lib.check(L.cb_pi_count_multi(2, harr, comms, n, 21, 4, 1, ctypes.byref(inside)))
+    assert inside.value == c_oracle.pi_inside(n, 21, 4, True)
+    for c in comms:
+        L.cb_comm_destroy(ctypes.c_void_p(c))
