@@ -52,6 +52,11 @@ PROTOTYPES = {
     "cb_free": (c_int, [c_void_p, c_void_p]),
     "cb_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size]),
     "cb_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size]),
+    "cb_memcpy_d2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size]),
+    "cb_memcpy_peer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size]),
+    "cb_cast": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_u64]),
+    "cb_unary": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_int, c_int]),
+    "cb_transpose": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_u64, c_int]),
     "cb_philox_words": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_u32, c_u64, c_u32]),
     "cb_rand_f32": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_u32]),
     "cb_rand_f64": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_u32]),
@@ -178,18 +183,11 @@ class Context:
         handle = c_void_p()
         check(lib().cb_ctx_create(self.device, c_void_p(stream) if stream else None, ctypes.byref(handle)))
         self.handle = handle
-        self._torch_stream = None
 
     @property
     def stream_ptr(self):
+        """The context's cudaStream_t as an integer (for frameworks that want to enqueue work behind the kernels)."""
         return lib().cb_ctx_stream(self.handle)
-
-    def torch_stream(self):
-        """The context's stream as a torch stream object (torch is the allocator/plumbing)."""
-        if self._torch_stream is None:
-            import torch
-            self._torch_stream = torch.cuda.ExternalStream(self.stream_ptr, device=torch.device("cuda", self.device))
-        return self._torch_stream
 
     def sync(self):
         check(lib().cb_ctx_sync(self.handle))

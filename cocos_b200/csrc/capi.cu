@@ -117,6 +117,12 @@ static int ctx_allocate(cb_ctx *c, void *stream_or_null) {
         c->own_stream = true;
     }
     CB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->dev));
+    {   // cb_malloc/cb_free: keep freed blocks in the device's default pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        CB_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->dev));
+        unsigned long long keep = ~0ull;
+        CB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CB_CUDA(cudaMalloc(&c->ws.partials, sizeof(double) * (size_t)kMaxGridBlocks * kMaxAcc));
     CB_CUDA(cudaMalloc(&c->ws.ticket, sizeof(unsigned int)));
     CB_CUDA(cudaMalloc(&c->ws.result, sizeof(double) * kMaxAcc));
@@ -221,17 +227,20 @@ extern "C" CB_API int cb_ctx_set_variant(cb_ctx *c, int variant) {
     return CB_OK;
 }
 
+// Device memory for the caller comes from the device's stream-ordered pool (cudaMallocAsync): allocation and release
+// are enqueued on the context's stream, cost no device synchronisation, and the pool keeps freed blocks for reuse
+// (release threshold = unlimited, set when the context is created) -- a caching allocator without a framework.
 extern "C" CB_API int cb_malloc(cb_ctx *c, size_t bytes, void **d_ptr) {
     CB_CTX(c);
     CB_REQUIRE(d_ptr != nullptr, "d_ptr is NULL");
-    CB_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    CB_CUDA(cudaMallocAsync(d_ptr, bytes ? bytes : 1, c->stream));
     return CB_OK;
 }
 
 extern "C" CB_API int cb_free(cb_ctx *c, void *d_ptr) {
     CB_CTX(c);
-    CB_CUDA(cudaStreamSynchronize(c->stream));
-    CB_CUDA(cudaFree(d_ptr));
+    if (d_ptr == nullptr) return CB_OK;
+    CB_CUDA(cudaFreeAsync(d_ptr, c->stream));      // ordered after every kernel already enqueued on the stream
     return CB_OK;
 }
 
@@ -246,6 +255,49 @@ extern "C" CB_API int cb_memcpy_d2h(cb_ctx *c, void *h_dst, const void *d_src, s
     CB_CTX(c);
     CB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
     CB_CUDA(cudaStreamSynchronize(c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_memcpy_d2d(cb_ctx *c, void *d_dst, const void *d_src, size_t bytes) {
+    CB_CTX(c);
+    CB_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return CB_OK;
+}
+
+// copy from another context's device (NVLink peer copy); ordered on the DESTINATION context's stream after the
+// source context's stream has drained
+extern "C" CB_API int cb_memcpy_peer(cb_ctx *dst_ctx, void *d_dst, cb_ctx *src_ctx, const void *d_src, size_t bytes) {
+    CB_REQUIRE(dst_ctx != nullptr && src_ctx != nullptr, "context is NULL");
+    CB_CUDA(cudaSetDevice(src_ctx->dev));
+    CB_CUDA(cudaStreamSynchronize(src_ctx->stream));
+    CB_CUDA(cudaSetDevice(dst_ctx->dev));
+    CB_CUDA(cudaMemcpyPeerAsync(d_dst, dst_ctx->dev, d_src, src_ctx->dev, bytes, dst_ctx->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_cast(cb_ctx *c, void *d_dst, int dst_kind, const void *d_src, int src_kind, uint64_t n) {
+    CB_CTX(c);
+    CB_REQUIRE((d_dst != nullptr && d_src != nullptr) || n == 0, "NULL device pointer");
+    CB_REQUIRE(dst_kind >= 0 && dst_kind <= 4 && src_kind >= 0 && src_kind <= 4,
+               "element kinds are 0 float32, 1 float64, 2 int32, 3 int64, 4 uint32");
+    CB_CUDA(launch_cast(d_dst, dst_kind, d_src, src_kind, n, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_unary(cb_ctx *c, void *d_dst, const void *d_src, uint64_t n, int op, int is_f64) {
+    CB_CTX(c);
+    CB_REQUIRE((d_dst != nullptr && d_src != nullptr) || n == 0, "NULL device pointer");
+    CB_REQUIRE(op == 0 || op == 1, "op must be 0 (exp) or 1 (log)");
+    CB_CUDA(launch_unary(d_dst, d_src, n, op, is_f64, c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_transpose(cb_ctx *c, void *d_dst, const void *d_src, uint64_t rows, uint64_t cols,
+                                   int elem_bytes) {
+    CB_CTX(c);
+    CB_REQUIRE((d_dst != nullptr && d_src != nullptr) || rows * cols == 0, "NULL device pointer");
+    CB_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "element size must be 4 or 8 bytes");
+    CB_CUDA(launch_transpose(d_dst, d_src, rows, cols, elem_bytes, c->stream));
     return CB_OK;
 }
 

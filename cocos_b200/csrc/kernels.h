@@ -157,6 +157,11 @@ cudaError_t launch_pi_count(uint64_t n, int antithetic, uint64_t draw_first, uin
                             int resident_blocks, ReduceWorkspace ws, cudaStream_t s);
 cudaError_t pi_occupancy(int antithetic, int *blocks_per_sm);
 
+// storage plumbing of the device array handle (array_kernels.cu); kinds: 0 f32, 1 f64, 2 i32, 3 i64, 4 u32
+cudaError_t launch_cast(void *dst, int dst_kind, const void *src, int src_kind, uint64_t n, cudaStream_t s);
+cudaError_t launch_unary(void *dst, const void *src, uint64_t n, int op, int is64, cudaStream_t s);   // op 0 exp, 1 log
+cudaError_t launch_transpose(void *dst, const void *src, uint64_t rows, uint64_t cols, int elem_bytes, cudaStream_t s);
+
 // calibration
 cudaError_t launch_peak_kernel(int kind, int sm_count, void *d_scratch, size_t scratch_bytes, double *work_done,
                                cudaStream_t s);

@@ -94,8 +94,6 @@ def call_payoff_sums(x_simulated: ndarray, strikes: tp.Sequence[float]) -> tp.Tu
     k_arr, nK = _lib.strikes_array(strikes)
     sums, sumsq = (ctypes.c_double * nK)(), (ctypes.c_double * nK)()
     fn = getattr(_lib.lib(), f"cb_call_payoff_sums_{_suffix(x_simulated.dtype)}")
-    if not x_simulated.tensor.is_contiguous():
-        raise ValueError("x_simulated must be contiguous")
     _lib.check(fn(ctx.handle, x_simulated.data_ptr, x_simulated.size, k_arr, nK, sums, sumsq))
     return np.array(sums), np.array(sumsq)
 

@@ -28,3 +28,26 @@ def array(obj, dtype=None) -> ndarray:
     if host.nbytes:
         _lib.check(_lib.lib().cb_memcpy_h2d(ctx.handle, out.data_ptr, host.ctypes.data, host.nbytes))
     return out
+
+
+def _unary(a: ndarray, op: int) -> ndarray:
+    import numpy as np
+    from .. import _lib
+    from ._array import empty_on
+    if not isinstance(a, ndarray):
+        raise TypeError("expected a cocos_b200 device array (no CPU branch)")
+    if a.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise TypeError("exp/log take float32 or float64 device arrays")
+    out = empty_on(a._ctx, a.shape, a.dtype)
+    _lib.check(_lib.lib().cb_unary(a._ctx.handle, out.data_ptr, a.data_ptr, a.size, op, int(a.dtype.itemsize == 8)))
+    return out
+
+
+def exp(a: ndarray) -> ndarray:
+    """Elementwise exp on the device (``cn.exp``): log prices -> prices before the density estimate."""
+    return _unary(a, 0)
+
+
+def log(a: ndarray) -> ndarray:
+    """Elementwise natural logarithm on the device (``cn.log``)."""
+    return _unary(a, 1)

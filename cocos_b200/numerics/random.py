@@ -314,8 +314,6 @@ def choice(a: ndarray, size: tp.Optional[tp.Union[tp.Tuple[int, ...], int]] = No
     index = randint(0, a.size, size=size)
     ctx = current_context()
     flat = a.reshape(-1)
-    if not flat.tensor.is_contiguous():
-        raise ValueError("a must be contiguous")
     out = empty_on(ctx, index.shape, a.dtype)
     _lib.check(_lib.lib().cb_gather(ctx.handle, out.data_ptr, flat.data_ptr, index.data_ptr, index.size,
                                     a.dtype.itemsize))

@@ -47,14 +47,15 @@ def compute_silverman_factor(kde_info: GaussianKDEInformation) -> float:
 
 def _to_device_rows(ctx, array, d_expected: tp.Optional[int] = None) -> ndarray:
     """(d, n) or (n,) input (NumPy or device) -> contiguous float32 device array of shape (n, d)."""
-    import torch
     if isinstance(array, ndarray):
-        t = array.tensor
-        if t.dim() == 1:
-            t = t.reshape(1, -1)
-        with torch.cuda.stream(ctx.torch_stream()):
-            rows = t.to(device=torch.device("cuda", ctx.device), dtype=torch.float32).t().contiguous()
-        out = ndarray(rows, ctx)
+        t = array.reshape(1, -1) if array.ndim == 1 else array
+        if t.ndim != 2:
+            raise ValueError("the dataset must be a (d, n) array or an (n,) vector")
+        if t.device_id != ctx.device:
+            t = t.copy_to(ctx)
+        if t.dtype != np.dtype(np.float32):
+            t = t.astype(np.float32)
+        out = t.reshape(t.shape[1], 1) if t.shape[0] == 1 else t.transpose()        # (d, n) -> (n, d)
     else:
         host = np.atleast_2d(np.asarray(array, dtype=np.float32))
         rows_h = np.ascontiguousarray(host.T)
@@ -166,12 +167,8 @@ class gaussian_kde:
     def _replica(self, ctx):
         """Whitened data (and weights) on ``ctx``'s device; copied once per device."""
         if ctx.device not in self._replicas:
-            import torch
-            with torch.cuda.stream(ctx.torch_stream()):
-                self._ctx.sync()
-                dev = torch.device("cuda", ctx.device)
-                wp = ndarray(self._whitened.tensor.to(dev), ctx)
-                ww = ndarray(self._weights_dev.tensor.to(dev), ctx) if self._weights_dev is not None else None
+            wp = self._whitened.copy_to(ctx)                    # NVLink peer copy, once per device
+            ww = self._weights_dev.copy_to(ctx) if self._weights_dev is not None else None
             self._replicas[ctx.device] = (wp, ww)
         return self._replicas[ctx.device]
 

@@ -13,7 +13,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 from cocos_b200.heston import simulate_heston_model                 # noqa: E402
-from cocos_b200.numerics._array import ndarray                      # noqa: E402
+import cocos_b200.numerics as cn                                    # noqa: E402
 from cocos_b200.scientific import gaussian_kde                      # noqa: E402
 
 
@@ -24,7 +24,7 @@ def main():
                                  x0=0.0, v0=0.101 ** 2)
     x._ctx.sync()
     print(f"simulated {R} paths x {nT - 1} steps in {(time.perf_counter() - t0) * 1e3:.2f} ms")
-    prices = ndarray(x.tensor.exp(), x._ctx)
+    prices = cn.exp(x)
     kde = gaussian_kde(prices)
     grid = np.linspace(0.4, 1.8, 1000)
     t0 = time.perf_counter()

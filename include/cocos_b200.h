@@ -84,11 +84,24 @@ CB_API int cb_ctx_set_launch(cb_ctx *ctx, int threads, int blocks_per_sm, int pa
  * variant computes the same stream and the same results */
 CB_API int cb_ctx_set_variant(cb_ctx *ctx, int variant);
 
-/* caller-side memory helpers for hosts that do not bring their own allocator */
+/* caller-side memory helpers for hosts that do not bring their own allocator: the storage behind the device array
+ * handle that stands in for cocos.numerics.ndarray (cocos/numerics/_array.py:150-171).  cb_malloc / cb_free are
+ * stream-ordered on the context's stream (the device's cudaMallocAsync pool, freed blocks are kept for reuse). */
 CB_API int cb_malloc(cb_ctx *ctx, size_t bytes, void **d_ptr);
 CB_API int cb_free(cb_ctx *ctx, void *d_ptr);
 CB_API int cb_memcpy_h2d(cb_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* synchronous */
 CB_API int cb_memcpy_d2h(cb_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* synchronous */
+CB_API int cb_memcpy_d2d(cb_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);   /* asynchronous, same device */
+/* device-to-device across contexts (ComputeDevicePool replicas: cocos/scientific/kde.py:698-767 ships the KDE to
+ * every worker); ordered on dst_ctx's stream after src_ctx's stream has drained */
+CB_API int cb_memcpy_peer(cb_ctx *dst_ctx, void *d_dst, cb_ctx *src_ctx, const void *d_src, size_t bytes);
+/* ndarray.astype (cocos/numerics/_array.py:221-228); kinds: 0 float32, 1 float64, 2 int32, 3 int64, 4 uint32 */
+CB_API int cb_cast(cb_ctx *ctx, void *d_dst, int dst_kind, const void *d_src, int src_kind, uint64_t n);
+/* exp (op 0) / log (op 1) of a float32 or float64 array: cn.exp(x_T) -> terminal prices, the step between the
+ * simulation and the density estimate in the reference's workflow (notebooks/Getting Started.ipynb cells 65-83) */
+CB_API int cb_unary(cb_ctx *ctx, void *d_dst, const void *d_src, uint64_t n, int op, int is_f64);
+/* 2-D transpose of a row-major rows x cols array of 4- or 8-byte elements (ndarray.T / transpose) */
+CB_API int cb_transpose(cb_ctx *ctx, void *d_dst, const void *d_src, uint64_t rows, uint64_t cols, int elem_bytes);
 
 /* ---- random arrays: cocos/numerics/random.py:127-153 (rand, randn) -------
  * Element order and stream layout are documented in DESIGN.md; `subsequence`

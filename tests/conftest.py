@@ -15,23 +15,40 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with `pytest -m gpu`)")
 
 
+def _source_hash(csrc):
+    """sha256 over the sources the Makefile lists, in its order (the Makefile writes the same into libcocos_b200.srchash)."""
+    import hashlib
+    import re
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    names = re.search(r"^SRCS\s*:=\s*(.*)$", mk, re.M).group(1).split() + \
+        re.search(r"^HDRS\s*:=\s*(.*)$", mk, re.M).group(1).split() + ["Makefile"]
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(csrc, n), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def pytest_sessionstart(session):
-    """(Re)build the CUDA library and the C oracle: both are git-ignored artefacts that nevertheless travel to the GPU
-    box, so a stale binary could otherwise be tested against newer sources.  `make` is incremental (a no-op when the
-    binaries are current); where the toolchain is absent (no nvcc / no make) an existing binary is used as it is."""
+    """Make sure the CUDA library and the C oracle are built FROM THE SOURCES AT HAND: both are git-ignored artefacts
+    that nevertheless travel to the GPU box, so a stale binary could otherwise be tested against newer sources.
+    The check is by content (a hash of the sources recorded at link time), not by mtime -- file times do not survive
+    the copy to the GPU box.  Where the toolchain is absent an up-to-date binary is required."""
     import shutil
     import subprocess
+    csrc = os.path.join(ROOT, "cocos_b200", "csrc")
     lib = os.path.join(ROOT, "cocos_b200", "libcocos_b200.so")
-    have_make = shutil.which("make") is not None
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if have_make and (os.path.exists(nvcc) or shutil.which("nvcc")):
-        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "cocos_b200", "csrc")])
-    elif not os.path.exists(lib):
-        raise RuntimeError("libcocos_b200.so is missing and there is no nvcc/make to build it")
-    if have_make and shutil.which("gcc"):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
-    elif not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
-        raise RuntimeError("oracle/liboracle.so is missing and there is no gcc/make to build it")
+    stamp = os.path.join(ROOT, "cocos_b200", "libcocos_b200.srchash")
+    current = os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read().strip() == _source_hash(csrc)
+    if not current:
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if shutil.which("make") is None or not (os.path.exists(nvcc) or shutil.which("nvcc")):
+            raise RuntimeError("libcocos_b200.so is missing or stale and there is no nvcc/make to rebuild it")
+        subprocess.check_call(["make", "-s", "-B", "-j8", "-C", csrc])
+    so = os.path.join(ROOT, "oracle", "liboracle.so")
+    src = os.path.join(ROOT, "oracle", "heston_oracle.c")
+    if not os.path.exists(so) or (os.path.getmtime(so) < os.path.getmtime(src) and shutil.which("gcc")):
+        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
 
 
 @pytest.fixture(scope="session")

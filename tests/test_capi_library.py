@@ -69,3 +69,18 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text, f
+
+
+def test_product_does_not_import_torch():
+    """libcocos_b200.so is the only native dependency of the product path: importing every product module (all but
+    the torchrun helper cocos_b200.distributed, which needs torch.distributed for the rendezvous) leaves torch out."""
+    import subprocess
+    import sys
+    code = ("import sys\n"
+            "import cocos_b200, cocos_b200.heston, cocos_b200.monte_carlo_pi, cocos_b200.device\n"
+            "import cocos_b200.numerics, cocos_b200.numerics.random, cocos_b200.numerics._array\n"
+            "import cocos_b200.scientific.kde, cocos_b200.multi_processing.device_pool\n"
+            "assert 'torch' not in sys.modules, 'torch was imported'\n"
+            "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

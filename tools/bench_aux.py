@@ -163,7 +163,8 @@ def main():
     x, _ = heston.simulate_heston_model(T=P["T"], N=101, R=2_000_000, mu=P["r"], kappa=P["kappa"], v_bar=P["v_bar"],
                                         sigma_v=P["sigma_v"], rho=P["rho"], x0=P["x0"], v0=P["v0"])
     ctx.sync()
-    prices = np.exp(x.to_numpy())
+    import cocos_b200.numerics as cn
+    prices = cn.exp(x)
     kde = gaussian_kde(prices)
     for m in (1000, 100_000):
         grid = np.linspace(0.3, 2.0, m)
