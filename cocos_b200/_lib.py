@@ -74,6 +74,8 @@ PROTOTYPES = {
     "cb_kde_moments_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_int, c_void_p]),
     "cb_kde_whiten_f32": (c_int, [c_void_p, c_void_p, c_u64, c_int, c_void_p, c_void_p]),
     "cb_kde_evaluate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_int, c_void_p, c_u64, c_double, c_void_p]),
+    "cb_kde_integrate_box_1d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_double, c_double, c_double, P(c_double)]),
+    "cb_kde_resample_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_int, c_void_p, c_u64, c_u64, c_u32, c_void_p]),
     "cb_heston_terminal_injected_f32": (c_int, [c_void_p, c_void_p, P(HestonParams), c_u64, c_u32, c_void_p, c_void_p]),
     "cb_heston_terminal_injected_f64": (c_int, [c_void_p, c_void_p, P(HestonParams), c_u64, c_u32, c_void_p, c_void_p]),
     "cb_heston_terminal_injected_host_f32": (c_int, [c_void_p, c_void_p, P(HestonParams), c_u64, c_u32, c_void_p, c_void_p]),

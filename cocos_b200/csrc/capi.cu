@@ -793,6 +793,35 @@ extern "C" CB_API int cb_kde_evaluate_f32(cb_ctx *c, const float *d_wpoints, con
     return CB_OK;
 }
 
+extern "C" CB_API int cb_kde_integrate_box_1d_f32(cb_ctx *c, const float *d_points, const float *d_weights_or_null,
+                                                  uint64_t n, double low, double high, double stdev, double *h_out) {
+    CB_CTX(c);
+    CB_REQUIRE(d_points != nullptr && h_out != nullptr, "NULL argument");
+    CB_REQUIRE(n >= 1 && stdev > 0.0, "empty dataset or non-positive bandwidth");
+    int rc = ensure_scratch(c, sizeof(double));
+    if (rc) return rc;
+    CB_CUDA(launch_kde_box_1d(d_points, d_weights_or_null, n, low, high, stdev, (double *)c->scratch, c->stream));
+    CB_CUDA(cudaMemcpyAsync(h_out, c->scratch, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));
+    return CB_OK;
+}
+
+extern "C" CB_API int cb_kde_resample_f32(cb_ctx *c, const float *d_points, const float *d_cumweights_or_null, uint64_t n,
+                                          int d, const float *h_chol, uint64_t size, uint64_t seed, uint32_t subsequence,
+                                          float *d_out) {
+    CB_CTX(c);
+    CB_REQUIRE(d_points != nullptr && h_chol != nullptr && (d_out != nullptr || size == 0), "NULL argument");
+    CB_REQUIRE(d >= 1 && d <= 4, "the resampling kernel supports 1 to 4 dimensions");
+    CB_REQUIRE(n >= 1, "empty dataset");
+    int rc = ensure_scratch(c, sizeof(float) * 16);
+    if (rc) return rc;
+    CB_CUDA(cudaMemcpyAsync(c->scratch, h_chol, sizeof(float) * d * d, cudaMemcpyHostToDevice, c->stream));
+    CB_CUDA(launch_kde_resample(d_points, d_cumweights_or_null, n, d, (const float *)c->scratch, size,
+                                philox_keys_from_seed(seed), subsequence, d_out, c->stream));
+    CB_CUDA(cudaStreamSynchronize(c->stream));      // h_chol is caller memory
+    return CB_OK;
+}
+
 // ---------------------------------------------------------------- Heston: parity kernels
 
 static int check_heston(const cb_heston_params *p, uint64_t R, uint32_t N) {

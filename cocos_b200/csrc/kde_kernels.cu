@@ -124,6 +124,94 @@ kde_finish_kernel(const float *__restrict__ partial, uint64_t m, int chunks, dou
     }
 }
 
+// integrate_box_1d (cocos/scientific/kde.py:869-902): sum_i w_i * (Phi((high - x_i)/s) - Phi((low - x_i)/s)) in double;
+// Phi(b) - Phi(a) = (erfc(a/sqrt2) - erfc(b/sqrt2)) / 2 keeps the tails accurate.  One atomic per block.
+__global__ void __launch_bounds__(256)
+kde_box_1d_kernel(const float *__restrict__ pts, const float *__restrict__ wts, uint64_t n, double low, double high,
+                  double inv_sd_sqrt2, double *__restrict__ out) {
+    double acc = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = (double)pts[i];
+        const double w = wts ? (double)wts[i] : 1.0;
+        acc += w * 0.5 * (erfc((low - x) * inv_sd_sqrt2) - erfc((high - x) * inv_sd_sqrt2));
+    }
+    __shared__ double s_acc[8];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double v = warp_sum(acc);
+    if (lane == 0) s_acc[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (unsigned w = 0; w < (blockDim.x >> 5); ++w) t += s_acc[w];
+        atomicAdd(out, t);
+    }
+}
+
+// resample (kde.py:987-1025): sample s = dataset[:, index_s] + L z_s with index_s ~ weights and z_s ~ N(0, I_d),
+// L = lower Cholesky factor of the kernel covariance.  One Philox4x32-10 block per sample (index = sample number):
+// words 2 and 3 pick the data point -- by binary search in the cumulative weights, or floor(u*n) for uniform
+// weights -- words 0 and 1 give the Box-Muller pair for dimensions 0 and 1; a second block (block = 1) of the same
+// counter feeds dimensions 2 and 3.  Output is (d, size) row-major like the reference's.
+__global__ void __launch_bounds__(256)
+kde_resample_kernel(const float *__restrict__ pts /* (n, d) */, const float *__restrict__ cumw /* (n) or NULL */,
+                    uint64_t n, int d, const float *__restrict__ chol /* d x d lower, row-major */, uint64_t size,
+                    const __grid_constant__ PhiloxKeys k, uint32_t subseq, float *__restrict__ out /* (d, size) */) {
+    __shared__ float s_l[16];
+    if (threadIdx.x < d * d) s_l[threadIdx.x] = chol[threadIdx.x];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < size; s += stride) {
+        const uint4 o = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), 0u, subseq, k);
+        // data point: 32 + 23 bits of uniform so that n up to 2^40 is resolved
+        uint64_t idx;
+        if (cumw == nullptr) {
+            const double u = ((double)o.w + (double)(o.z >> 9) * (1.0 / 8388608.0)) * (1.0 / 4294967296.0);   // [0,1)
+            idx = (uint64_t)(u * (double)n);
+            if (idx >= n) idx = n - 1;
+        } else {
+            const float u = u01_f32(o.w) * cumw[n - 1];
+            uint64_t lo = 0, hi = n - 1;                       // first i with cumw[i] > u
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (cumw[mid] > u) hi = mid; else lo = mid + 1;
+            }
+            idx = lo;
+        }
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        box_muller(o.x, o.y, -1.3862943611198906f, kTwoPi, z[0], z[1]);
+        if (d > 2) {
+            const uint4 o2 = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), 1u, subseq, k);
+            box_muller(o2.x, o2.y, -1.3862943611198906f, kTwoPi, z[2], z[3]);
+        }
+        for (int a = 0; a < d; ++a) {
+            float t = pts[idx * d + a];
+            for (int b = 0; b <= a; ++b) t = fmaf(s_l[a * d + b], z[b], t);
+            out[(uint64_t)a * size + s] = t;
+        }
+    }
+}
+
+cudaError_t launch_kde_box_1d(const float *d_pts, const float *d_w, uint64_t n, double low, double high, double sd,
+                              double *d_out, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    uint64_t b = (n + 255) / 256;
+    if (b > 148ull * 8) b = 148ull * 8;
+    if (b < 1) b = 1;
+    kde_box_1d_kernel<<<(int)b, 256, 0, s>>>(d_pts, d_w, n, low, high, 1.0 / (sd * 1.4142135623730951), d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kde_resample(const float *d_pts, const float *d_cumw, uint64_t n, int d, const float *d_chol,
+                                uint64_t size, const PhiloxKeys &k, uint32_t subseq, float *d_out, cudaStream_t s) {
+    if (size == 0) return cudaSuccess;
+    uint64_t b = (size + 255) / 256;
+    if (b > 148ull * 8) b = 148ull * 8;
+    kde_resample_kernel<<<(int)b, 256, 0, s>>>(d_pts, d_cumw, n, d, d_chol, size, k, subseq, d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_kde_moments(const float *d_pts, const float *d_w, uint64_t n, int d, double *d_out,
                                cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(double) * (1 + d + d * d), s);

@@ -2,8 +2,9 @@
 
 Mirrors ``gaussian_kde`` (kde.py:414-1170, itself adapted from SciPy): constructor arguments, ``d / n / factor /
 covariance / inv_cov / weights / neff``, ``evaluate`` (= ``__call__`` = ``pdf``), ``logpdf``,
-``evaluate_in_batches``, ``evaluate_in_batches_on_multiple_devices`` and the module-level
-``evaluate_gaussian_kde_in_batches`` (kde.py:1205-1232).  Not built: ``integrate_*``, ``resample``, ``set_bandwidth``.
+``evaluate_in_batches``, ``evaluate_in_batches_on_multiple_devices``, ``integrate_gaussian``, ``integrate_box_1d``,
+``integrate_kde``, ``resample`` (kde.py:816-1025) and the module-level ``evaluate_gaussian_kde_in_batches``
+(kde.py:1205-1232).
 
 The reference whitens the data with cholesky(inv_cov) and evaluates
 ``norm * sum_i w_i exp(-|p_i - q_j|^2 / 2)`` by materialising an (n, m, d) array per batch (kde.py:152-197).  Here the
@@ -207,6 +208,91 @@ class gaussian_kde:
 
     def logpdf(self, x) -> np.ndarray:
         return np.log(self.evaluate(x).to_numpy())
+
+    # ---- integrals and resampling (kde.py:816-1025) --------------------------------------------------------
+    def _gaussian_sums(self, sum_cov: np.ndarray, centres: np.ndarray) -> np.ndarray:
+        """For every column c of ``centres`` (d, m): sum_i w_i exp(-(x_i - c)^T sum_cov^-1 (x_i - c) / 2) / norm, with
+        norm = (2 pi)^(d/2) sqrt(det sum_cov) -- the dataset whitened with cholesky(sum_cov^-1) and pushed through the
+        evaluation kernel (one MUFU.EX2 per (data point, centre) pair)."""
+        ctx = self._ctx
+        L = _lib.lib()
+        d = self.d
+        chol = np.linalg.cholesky(sum_cov)                               # raises LinAlgError if not s.p.d.
+        norm_const = (2 * np.pi) ** (d / 2.0) * float(np.prod(np.diag(chol)))
+        whitening = np.linalg.cholesky(np.linalg.inv(sum_cov))
+        matrix = np.ascontiguousarray(whitening * _PRESCALE, dtype=np.float32)
+        white = empty_on(ctx, (self.n, d), np.float32)
+        _lib.check(L.cb_kde_whiten_f32(ctx.handle, self._points.data_ptr, self.n, d, matrix.ctypes.data, white.data_ptr))
+        m = centres.shape[1]
+        xi = np.ascontiguousarray(centres.T.astype(np.float64) @ (whitening * _PRESCALE), dtype=np.float32)
+        d_xi = empty_on(ctx, (m, d), np.float32)
+        _lib.check(L.cb_memcpy_h2d(ctx.handle, d_xi.data_ptr, xi.ctypes.data, xi.nbytes))
+        out = empty_on(ctx, (m,), np.float32)
+        scale = (1.0 if self._weights is not None else 1.0 / self.n) / norm_const
+        _lib.check(L.cb_kde_evaluate_f32(ctx.handle, white.data_ptr,
+                                         self._weights_dev.data_ptr if self._weights_dev is not None else None,
+                                         self.n, d, d_xi.data_ptr, m, scale, out.data_ptr))
+        return out.to_numpy().astype(np.float64)
+
+    def integrate_gaussian(self, mean, cov) -> float:
+        """Multiply the estimated density by a multivariate Gaussian and integrate over the whole space."""
+        mean = np.atleast_1d(np.squeeze(np.asarray(mean, dtype=np.float64)))
+        cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+        if mean.shape != (self.d,):
+            raise ValueError("mean does not have dimension %s" % self.d)
+        if cov.shape != (self.d, self.d):
+            raise ValueError("covariance does not have dimension %s" % self.d)
+        return float(self._gaussian_sums(self.covariance + cov, mean[:, None])[0])
+
+    def integrate_box_1d(self, low, high) -> float:
+        """Integral of a 1-D estimate between two bounds."""
+        if self.d != 1:
+            raise ValueError("integrate_box_1d() only handles 1D pdfs")
+        stdev = float(np.sqrt(self.covariance).ravel()[0])
+        value = ctypes.c_double(0.0)
+        _lib.check(_lib.lib().cb_kde_integrate_box_1d_f32(
+            self._ctx.handle, self._points.data_ptr,
+            self._weights_dev.data_ptr if self._weights_dev is not None else None, self.n, float(low), float(high),
+            stdev, ctypes.byref(value)))
+        return value.value if self._weights is not None else value.value / self.n
+
+    def integrate_kde(self, other: "gaussian_kde") -> float:
+        """Integral of the product of this estimate with another one."""
+        if other.d != self.d:
+            raise ValueError("KDEs are not the same dimensionality")
+        small, large = (other, self) if other.n < self.n else (self, other)
+        centres = small._points.to_numpy().T.astype(np.float64)          # (d, n_small)
+        sums = large._gaussian_sums(small.covariance + large.covariance, centres)
+        return float(np.dot(sums, small.weights.astype(np.float64)))
+
+    def resample(self, size: tp.Optional[int] = None, seed: tp.Optional[int] = None) -> ndarray:
+        """Randomly sample a dataset from the estimated pdf: device array of shape (d, size).
+
+        ``seed`` = None draws from the module generator (``cocos_b200.numerics.random``); an integer gives a
+        reproducible draw without touching it (the reference accepts NumPy generators here; the device stream is
+        Philox, so only integer seeds carry over)."""
+        from ..numerics import random as _random
+        if size is None:
+            size = int(self.neff)
+        size = int(size)
+        if seed is None:
+            seed_value, sub = _random.get_seed(), _random.next_subsequence()
+        elif isinstance(seed, numbers.Integral):
+            seed_value, sub = int(seed), 0
+        else:
+            raise TypeError("seed must be None or an integer (the device generator is Philox4x32-10)")
+        ctx = self._ctx
+        if self._weights is not None and getattr(self, "_cumweights_dev", None) is None:
+            cum = np.cumsum(self._weights.astype(np.float64)).astype(np.float32)
+            self._cumweights_dev = empty_on(ctx, (self.n,), np.float32)
+            _lib.check(_lib.lib().cb_memcpy_h2d(ctx.handle, self._cumweights_dev.data_ptr, cum.ctypes.data, cum.nbytes))
+        chol = np.ascontiguousarray(np.linalg.cholesky(self.covariance), dtype=np.float32)
+        out = empty_on(ctx, (self.d, size), np.float32)
+        _lib.check(_lib.lib().cb_kde_resample_f32(
+            ctx.handle, self._points.data_ptr,
+            self._cumweights_dev.data_ptr if self._weights is not None else None, self.n, self.d, chol.ctypes.data,
+            size, seed_value, sub, out.data_ptr))
+        return out
 
     def evaluate_in_batches(self, points, maximum_number_of_elements_per_batch: int) -> np.ndarray:
         """Evaluate in batches of at most max/(n*d) points; results in main memory (kde.py:670-696)."""

@@ -153,6 +153,15 @@ CB_API int cb_kde_moments_f32(cb_ctx *ctx, const float *d_points, const float *d
 CB_API int cb_kde_whiten_f32(cb_ctx *ctx, const float *d_in, uint64_t n, int d, const float *h_matrix, float *d_out);
 CB_API int cb_kde_evaluate_f32(cb_ctx *ctx, const float *d_wpoints, const float *d_weights_or_null, uint64_t n, int d,
                                const float *d_wxi, uint64_t m, double scale, float *d_out);
+/* integrate_box_1d (kde.py:869-902): sum_i w_i (Phi((high-x_i)/stdev) - Phi((low-x_i)/stdev)), d_points = the raw 1-D
+ * dataset (n floats), weights NULL = 1 each (the caller divides by n); accumulated in double */
+CB_API int cb_kde_integrate_box_1d_f32(cb_ctx *ctx, const float *d_points, const float *d_weights_or_null, uint64_t n,
+                                       double low, double high, double stdev, double *h_out);
+/* resample (kde.py:987-1025): d_out (d, size) row-major = dataset[:, index] + chol @ z with index drawn from the
+ * weights (d_cumweights = inclusive cumulative sums, NULL = uniform) and z ~ N(0, I); h_chol = LOWER Cholesky factor
+ * of the kernel covariance (host, row-major d x d); one Philox block per sample */
+CB_API int cb_kde_resample_f32(cb_ctx *ctx, const float *d_points, const float *d_cumweights_or_null, uint64_t n, int d,
+                               const float *h_chol, uint64_t size, uint64_t seed, uint32_t subsequence, float *d_out);
 
 /* ---- Heston paths ---------------------------------------------------------
  * Parity kernels: simulate_heston_model (heston_utilities.py:58-96) with the

@@ -97,3 +97,66 @@ def test_heston_terminal_prices_workflow(kde_mod, ref_params):
     ref = ss.gaussian_kde(prices.to_numpy().astype(np.float64)).evaluate(grid)
     np.testing.assert_allclose(dens, ref, rtol=2e-4, atol=1e-7)
     assert abs(np.trapezoid(dens, grid) - 1.0) < 1e-3
+
+
+# ---- integrals and resampling (cocos/scientific/kde.py:816-1025): SciPy is the truth, as in the reference's own test
+
+def _datasets():
+    rng = np.random.default_rng(5)
+    one = np.concatenate([rng.normal(0.0, 1.0, 3000), rng.normal(3.0, 0.5, 2000)])
+    two = rng.multivariate_normal([0.0, 1.0], [[1.0, 0.6], [0.6, 2.0]], size=4000).T
+    w = rng.uniform(0.2, 1.0, one.size)
+    return one, two, w
+
+
+def test_integrate_gaussian_box_and_kde_match_scipy(kde_mod):
+    one, two, w = _datasets()
+    for data, weights in ((one, None), (one, w), (two, None)):
+        k = kde_mod.gaussian_kde(data, weights=weights)
+        ref = ss.gaussian_kde(data, weights=weights)
+        d = k.d
+        mean = np.full(d, 0.3)
+        cov = np.eye(d) * 0.7 + 0.1
+        assert k.integrate_gaussian(mean, cov) == pytest.approx(ref.integrate_gaussian(mean, cov), rel=2e-4)
+        other_data = data[..., ::3] + 0.25
+        ko, ro = kde_mod.gaussian_kde(other_data), ss.gaussian_kde(other_data)
+        assert k.integrate_kde(ko) == pytest.approx(ref.integrate_kde(ro), rel=2e-4)
+        assert ko.integrate_kde(k) == pytest.approx(ref.integrate_kde(ro), rel=2e-4)        # symmetric
+        if d == 1:
+            for low, high in ((-1.0, 2.0), (-np.inf, 0.5), (2.5, np.inf), (-40.0, 40.0), (6.0, 7.0)):
+                assert k.integrate_box_1d(low, high) == pytest.approx(ref.integrate_box_1d(low, high), rel=1e-5, abs=1e-9)
+        else:
+            with pytest.raises(ValueError):
+                k.integrate_box_1d(0.0, 1.0)
+    k1 = kde_mod.gaussian_kde(one)
+    with pytest.raises(ValueError):
+        k1.integrate_gaussian([0.0, 1.0], np.eye(2))
+    with pytest.raises(ValueError):
+        k1.integrate_kde(kde_mod.gaussian_kde(two))
+
+
+def test_resample_follows_the_estimated_density(kde_mod):
+    """Samples from the estimate: the right shape, reproducible with a seed, mean/covariance of the mixture
+    (data moments + kernel covariance), and in 1-D a KS test against the estimate's own CDF (integrate_box_1d)."""
+    one, two, w = _datasets()
+    for data, weights in ((one, None), (one, w), (two, None)):
+        k = kde_mod.gaussian_kde(data, weights=weights)
+        size = 400_000
+        s1 = k.resample(size, seed=11).to_numpy()
+        assert s1.shape == (k.d, size)
+        assert np.array_equal(s1, k.resample(size, seed=11).to_numpy())
+        assert not np.array_equal(s1, k.resample(size, seed=12).to_numpy())
+        assert k.resample().shape == (k.d, int(k.neff))
+        data2 = np.atleast_2d(data)
+        wn = k.weights.astype(np.float64) / np.sum(k.weights)
+        mean = data2 @ wn
+        cov = (data2 - mean[:, None]) @ np.diag(wn) @ (data2 - mean[:, None]).T + k.covariance
+        np.testing.assert_allclose(s1.mean(axis=1), mean, atol=6 * np.sqrt(np.diag(cov) / size))
+        np.testing.assert_allclose(np.cov(s1), np.squeeze(cov), rtol=0.02, atol=0.01)
+        if k.d == 1:
+            ref = ss.gaussian_kde(data, weights=weights)
+            sample = s1[0, :20_000].astype(np.float64)
+            grid = np.linspace(sample.min() - 1, sample.max() + 1, 2001)
+            cdf = np.array([ref.integrate_box_1d(-np.inf, g) for g in grid])
+            stat, pvalue = ss.kstest(sample, lambda x: np.interp(x, grid, cdf))
+            assert pvalue > 0.001, (stat, pvalue)

@@ -2,6 +2,7 @@
 one Philox block is split into three (radius 23 bit, angle 19 bit) pairs that share word 3 for the low angle bits,
 so independence ACROSS the three steps of a block is worth testing, not just marginal normality."""
 import numpy as np
+import pytest
 from scipy import stats
 
 from oracle import heston_numpy as hn, philox_numpy as px
@@ -55,3 +56,43 @@ def test_consecutive_blocks_and_pairs_are_uncorrelated():
     a, b = half(2)[:, 0], half(3)[:, 0]             # last step of block 0, first step of block 1
     assert abs(np.corrcoef(a, b)[0, 1]) < 4.5 / np.sqrt(N)
     assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 4.5 / np.sqrt(N)          # neighbouring pairs (counters i, i+1)
+
+
+@pytest.mark.gpu
+def test_f32_bias_is_below_the_c4_standard_error(gpu_device):
+    """float32 state + MUFU arithmetic against (a) the float64 kernel and (b) the oracle's exact-libm float64 model,
+    both on the SAME Philox stream at nT = 1001 (C4's step count): the paired mean payoff difference must be far
+    below the 1.9e-6 standard error C4 (1e9 paths) reports.  tools/bias_f32.py runs the same at 1e8 paths."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bias_f32
+    ctx = gpu_device.current_context()
+    a = bias_f32.paired(ctx, 2_000_000, 1001, chunk=1_000_000)
+    assert abs(a["mean_payoff_difference_f32_minus_f64"]) < 1.0e-6 + 4 * a["standard_error"], a
+    assert abs(a["kernel_sums_difference_per_path"]) < 1.5e-6 + 4 * a["standard_error"], a
+    assert a["max_abs_x_difference"] < 5e-4, a
+    b = bias_f32.against_oracle(ctx, 100_000, 1001)
+    assert abs(b["mean_payoff_difference_f32_minus_exact_model"]) < 1.0e-6 + 4 * b["standard_error"], b
+
+
+@pytest.mark.gpu
+def test_normal_tails_up_to_the_radius_cap(gpu_device):
+    """Counts of |z| > t over 2^28 draws of the kernel's Box-Muller against n*erfc(t/sqrt2); nothing beyond the cap
+    sqrt(46 ln 2) = 5.6467 (23-bit radius), as DESIGN.md states.  tools/tail_counts.py runs 2^30 draws."""
+    import ctypes
+    import math
+    from cocos_b200 import _lib
+    from cocos_b200.numerics._array import empty_on
+    ctx = gpu_device.current_context()
+    n = 1 << 28
+    buf = empty_on(ctx, (n,), np.float32)
+    _lib.check(_lib.lib().cb_randn_f32(ctx.handle, buf.data_ptr, n, 99, 1))
+    z = np.abs(buf.to_numpy())
+    assert z.max() <= math.sqrt(46 * math.log(2.0)) * (1 + 1e-5)
+    for t in (3.0, 4.0, 4.5, 5.0):
+        expected = n * math.erfc(t / math.sqrt(2.0))
+        got = int(np.count_nonzero(z > t))
+        assert abs(got - expected) < 5 * math.sqrt(expected) + 0.12 * expected * (t >= 5.0), (t, got, expected)
+    m2 = float(np.dot(z.astype(np.float64), z.astype(np.float64)) / n)
+    assert abs(m2 - 1.0) < 5 * math.sqrt(2.0 / n) + 3e-6
