@@ -151,7 +151,7 @@ def test_resample_follows_the_estimated_density(kde_mod):
         wn = k.weights.astype(np.float64) / np.sum(k.weights)
         mean = data2 @ wn
         cov = (data2 - mean[:, None]) @ np.diag(wn) @ (data2 - mean[:, None]).T + k.covariance
-        np.testing.assert_allclose(s1.mean(axis=1), mean, atol=6 * np.sqrt(np.diag(cov) / size))
+        assert np.all(np.abs(s1.mean(axis=1) - mean) < 6 * np.sqrt(np.diag(np.atleast_2d(cov)) / size))
         np.testing.assert_allclose(np.cov(s1), np.squeeze(cov), rtol=0.02, atol=0.01)
         if k.d == 1:
             ref = ss.gaussian_kde(data, weights=weights)
