@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcocos_b200.so")
+# $COCOS_B200_LIBRARY names another build of the same sources (A/B runs of tuning variants); default: the in-tree one
+LIB_PATH = os.environ.get("COCOS_B200_LIBRARY") or os.path.join(_HERE, "libcocos_b200.so")
 
 c_int, c_u32, c_u64, c_size = ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_size_t
 c_void_p, c_char_p, c_double, c_float = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double, ctypes.c_float

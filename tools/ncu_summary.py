@@ -1,4 +1,6 @@
-"""Summarise an .ncu-rep (one kernel launch) as markdown: python tools/ncu_summary.py report.ncu-rep "title" > out.md"""
+"""Summarise one kernel launch of an .ncu-rep as markdown:
+python tools/ncu_summary.py report.ncu-rep "title" [kernel-name substring [occurrence]] > out.md
+(default: the first launch in the report; occurrence counts matching launches from 0)"""
 import csv
 import io
 import subprocess
@@ -7,7 +9,12 @@ import sys
 rep, title = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, d = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+want = sys.argv[3] if len(sys.argv) > 3 else None
+nth = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+name_col = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
+matches = [r for r in rows[2:] if want is None or (name_col is not None and want in r[name_col])]
+d = matches[nth]
 m = {h: (d[i], units[i]) for i, h in enumerate(hdr)}
 keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__occupancy_limit_registers", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
@@ -20,6 +27,7 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_active.avg.per_cycle_active",
         "smsp__warps_eligible.avg.per_cycle_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
