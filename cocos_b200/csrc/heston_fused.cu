@@ -34,10 +34,7 @@ __global__ void __launch_bounds__(kMaxThreads, MINB)
 heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace ws,
                     real *__restrict__ x_out, real *__restrict__ v_out) {
     const uint64_t total = (uint64_t)gridDim.x * blockDim.x;
-    // slot of this thread in a grid-stride round, warp-interleaved across the blocks: warp w of block b takes the 32
-    // slots of warp-slot w*gridDim.x + b.  A partial last round (small shards: strong scaling) then keeps the FIRST
-    // warps of EVERY block busy instead of all warps of the first blocks, i.e. every SM gets the same share of the tail.
-    const uint64_t gtid = ((uint64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t per_iter = total * PPT;
     const uint64_t iters = (c.pair_count + per_iter - 1) / per_iter;   // same for every thread: warps stay converged
     const uint32_t lane = threadIdx.x & 31;
