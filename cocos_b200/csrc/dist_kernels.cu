@@ -8,6 +8,7 @@
 // Philox counter: element e of a launch uses index = e / 4 (simple kinds) or index = e (rejection kinds) and
 // block = attempt, so results do not depend on the launch geometry.  CPU model: oracle/distributions_numpy.py.
 #include "kernels.h"
+#include "fill_loop.cuh"
 
 namespace cb {
 
@@ -47,46 +48,51 @@ __device__ __forceinline__ float gamma_any(float alpha, uint32_t ilo, uint32_t i
     return gamma_mt(alpha + 1.0f, ilo, ihi, stream, subseq, k) * boost;
 }
 
+// the four values of one Philox block for the simple kinds
+template <int KIND>
+__device__ __forceinline__ void dist_values(const uint4 &o, float a, float b, float (&v)[4]) {
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+    if constexpr (KIND == kNormal || KIND == kLognormal) {
+        box_muller(o.x, o.y, -1.3862943611198906f, kTwoPi, v[0], v[1]);
+        box_muller(o.z, o.w, -1.3862943611198906f, kTwoPi, v[2], v[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = fmaf(b, v[e], a);                                   // loc + scale*z
+            if constexpr (KIND == kLognormal) v[e] = __expf(v[e]);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if constexpr (KIND == kUniform) {
+                v[e] = __fadd_rn(__fmul_rn(u01_f32(w[e]), b), a);      // u*(high-low)+low, reference roundings
+            } else if constexpr (KIND == kExponential) {
+                v[e] = -a * __logf(__fsub_rn(1.0f, u01_f32(w[e])));    // log(1-u)*(-scale), 1-u in (0,1]
+            } else {                                                   // logistic: loc - scale*log(1/u - 1)
+                const float u = u_open(w[e]);
+                v[e] = a + b * __logf(__fdividef(u, 1.0f - u));
+            }
+        }
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
 dist_fill_kernel(float *__restrict__ out, uint64_t n, float a, float b, const __grid_constant__ PhiloxKeys k,
                  uint32_t subseq) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     if constexpr (KIND <= kLogistic) {
+        if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {            // the shared fast loop (fill_loop.cuh)
+            philox_fill_aligned<float, 4>(out, n, k, subseq,
+                                          [a, b](const uint4 &o, float (&v)[4]) { dist_values<KIND>(o, a, b, v); });
+            return;
+        }
         const uint64_t n_blocks = (n + 3) / 4;
-        const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
         for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_blocks; j += stride) {
-            const uint4 o = philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, subseq, k);
-            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
             float v[4];
-            if constexpr (KIND == kNormal || KIND == kLognormal) {
-                box_muller(o.x, o.y, -1.3862943611198906f, kTwoPi, v[0], v[1]);
-                box_muller(o.z, o.w, -1.3862943611198906f, kTwoPi, v[2], v[3]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    v[e] = fmaf(b, v[e], a);                                   // loc + scale*z
-                    if constexpr (KIND == kLognormal) v[e] = __expf(v[e]);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if constexpr (KIND == kUniform) {
-                        v[e] = __fadd_rn(__fmul_rn(u01_f32(w[e]), b), a);      // u*(high-low)+low, reference roundings
-                    } else if constexpr (KIND == kExponential) {
-                        v[e] = -a * __logf(__fsub_rn(1.0f, u01_f32(w[e])));    // log(1-u)*(-scale), 1-u in (0,1]
-                    } else {                                                   // logistic: loc - scale*log(1/u - 1)
-                        const float u = u_open(w[e]);
-                        v[e] = a + b * __logf(__fdividef(u, 1.0f - u));
-                    }
-                }
-            }
+            dist_values<KIND>(philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, subseq, k), a, b, v);
             const uint64_t base = j * 4;
-            if (aligned && base + 4 <= n) {
-                __stcs(reinterpret_cast<float4 *>(out + base), make_float4(v[0], v[1], v[2], v[3]));
-            } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (base + e < n) out[base + e] = v[e];
-            }
+            for (int e = 0; e < 4; ++e) if (base + e < n) out[base + e] = v[e];
         }
     } else {
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -170,13 +176,14 @@ static int dist_grid(uint64_t work) {
 cudaError_t launch_dist_fill(int kind, float *d_out, uint64_t n, float a, float b, const PhiloxKeys &k,
                              uint32_t subseq, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    const int g4 = dist_grid((n + 3) / 4), g1 = dist_grid(n);
+    const uint64_t g4_blocks = ((n + 3) / 4 + 511) / 512;      // two Philox blocks per thread and trip (fill_loop.cuh)
+    const int g1 = dist_grid(n);
     switch (kind) {
-        case kUniform: dist_fill_kernel<kUniform><<<g4, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
-        case kExponential: dist_fill_kernel<kExponential><<<g4, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
-        case kNormal: dist_fill_kernel<kNormal><<<g4, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
-        case kLognormal: dist_fill_kernel<kLognormal><<<g4, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
-        case kLogistic: dist_fill_kernel<kLogistic><<<g4, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
+        case kUniform: dist_fill_kernel<kUniform><<<resident_grid((const void *)dist_fill_kernel<kUniform>, g4_blocks), 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
+        case kExponential: dist_fill_kernel<kExponential><<<resident_grid((const void *)dist_fill_kernel<kExponential>, g4_blocks), 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
+        case kNormal: dist_fill_kernel<kNormal><<<resident_grid((const void *)dist_fill_kernel<kNormal>, g4_blocks), 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
+        case kLognormal: dist_fill_kernel<kLognormal><<<resident_grid((const void *)dist_fill_kernel<kLognormal>, g4_blocks), 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
+        case kLogistic: dist_fill_kernel<kLogistic><<<resident_grid((const void *)dist_fill_kernel<kLogistic>, g4_blocks), 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
         case kWald: dist_fill_kernel<kWald><<<g1, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
         case kGamma: dist_fill_kernel<kGamma><<<g1, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;
         case kBeta: dist_fill_kernel<kBeta><<<g1, 256, 0, s>>>(d_out, n, a, b, k, subseq); break;

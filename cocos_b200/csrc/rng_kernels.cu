@@ -12,11 +12,8 @@
 //   f64: elements 2j, 2j+1 from Philox(index=j): uniform u52(o0,o1), u52(o2,o3);
 //        normal: one Box-Muller pair from U = 1-u52(o0,o1), t = u52(o2,o3)
 // Each thread produces 16 bytes per Philox call and stores them as one vector.
-#include <map>
-#include <mutex>
-#include <type_traits>
-
 #include "kernels.h"
+#include "fill_loop.cuh"
 
 namespace cb {
 
@@ -95,61 +92,12 @@ random_fill_kernel(real *__restrict__ out, uint64_t n, const __grid_constant__ P
     }
 }
 
-// The fast path of random_fill_kernel for a 16-byte aligned output: same elements, but
-//   * rounds 0 and 1 of Philox cost one multiply each (UniformTail: three of the four counter words are uniform),
-//     round keys live in registers;
-//   * the 64-bit block index is cut into segments with a uniform high word, inside which a thread owns the blocks
-//     first + gtid + t*stride: 32-bit arithmetic, a trip count known up front, no bounds test per block and one
-//     64-bit pointer bump per trip; two Philox calls per trip are independent chains for the scheduler;
-//   * the ragged last block (n not a multiple of W) is written by one thread with scalar stores.
+// The fast path of random_fill_kernel for a 16-byte aligned output (philox_fill_aligned, fill_loop.cuh): same elements.
 template <typename real, bool NORMAL>
 __global__ void __launch_bounds__(256)
 random_fill_fast_kernel(real *__restrict__ out, uint64_t n, const __grid_constant__ PhiloxKeys kc, uint32_t subseq) {
     using D = Draw<real, NORMAL>;
-    constexpr int W = D::W;
-    using vec_t = typename std::conditional<W == 4, float4, double2>::type;
-    PhiloxKeys k;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) { k.k0[r] = pin(kc.k0[r]); k.k1[r] = pin(kc.k1[r]); }
-    const uint64_t full = n / W;                              // whole blocks: one 16-byte vector each
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    auto store = [](vec_t *dst, const real (&v)[W]) {
-        if constexpr (W == 4) __stcs(dst, make_float4(v[0], v[1], v[2], v[3]));
-        else __stcs(dst, make_double2(v[0], v[1]));
-    };
-    for (uint64_t seg = 0; seg < full;) {
-        const uint32_t hi = (uint32_t)(seg >> 32);
-        const uint64_t seg_end = ((uint64_t)hi + 1) << 32 < full ? ((uint64_t)hi + 1) << 32 : full;
-        const uint64_t span = seg_end - seg;
-        UniformTail tail;
-        tail.init(hi, subseq, k);
-        const uint64_t mine = span > gtid ? (span - gtid + stride - 1) / stride : 0;
-        uint32_t c0 = (uint32_t)seg + gtid;
-        vec_t *dst = reinterpret_cast<vec_t *>(out) + seg + gtid;
-        for (uint32_t t = (uint32_t)(mine >> 1); t > 0; --t) {
-            real va[W], vb[W];
-            const uint4 a = tail.call(c0, k);
-            const uint4 b = tail.call(c0 + stride, k);
-            D::make(a, va);
-            D::make(b, vb);
-            store(dst, va);
-            store(dst + stride, vb);
-            c0 += 2u * stride;
-            dst += 2ull * stride;
-        }
-        if (mine & 1) {
-            real va[W];
-            D::make(tail.call(c0, k), va);
-            store(dst, va);
-        }
-        seg = seg_end;
-    }
-    if (gtid == 0 && full * W < n) {                          // the ragged last block
-        real v[W];
-        D::make(philox4x32_10((uint32_t)full, (uint32_t)(full >> 32), 0u, subseq, k), v);
-        for (int e = 0; e < W; ++e) if (full * W + e < n) out[full * W + e] = v[e];
-    }
+    philox_fill_aligned<real, D::W>(out, n, kc, subseq, [](const uint4 &o, real (&v)[D::W]) { D::make(o, v); });
 }
 
 // Output shape (outer, d, inner) row-major, antithetic along the middle axis:
@@ -275,27 +223,6 @@ static int fill_grid(uint64_t n_blocks) {
     if (b < 1) b = 1;
     const uint64_t cap = 148ull * 8 * 4;
     return (int)(b > cap ? cap : b);
-}
-
-// grid of the fast fills: every block the device can hold at once (occupancy query, cached per kernel), each thread
-// then walks its strided share of the Philox blocks
-static int resident_grid(const void *fn, uint64_t blocks_wanted) {
-    static std::map<const void *, int> cache;
-    static std::mutex lock;
-    int resident = 0;
-    {
-        std::lock_guard<std::mutex> g(lock);
-        auto it = cache.find(fn);
-        if (it == cache.end()) {
-            int dev = 0, sms = 148, bps = 8;
-            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, 256, 0) != cudaSuccess || bps < 1) bps = 1;
-            it = cache.emplace(fn, sms * bps).first;
-        }
-        resident = it->second;
-    }
-    if (blocks_wanted < 1) blocks_wanted = 1;
-    return (int)(blocks_wanted < (uint64_t)resident ? blocks_wanted : (uint64_t)resident);
 }
 
 cudaError_t launch_philox_words(uint32_t *d_out, uint64_t n_blocks, uint64_t first, uint32_t block,

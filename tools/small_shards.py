@@ -1,3 +1,4 @@
+"""Pricing pass on small shards (what one of 8 GPUs gets when C3 is strong-scaled) against block size: python tools/small_shards.py"""
 import ctypes, sys, os, math
 sys.path.insert(0, os.getcwd())
 from cocos_b200 import _lib, device
