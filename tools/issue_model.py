@@ -23,7 +23,6 @@ SMSP = 148 * 4
 KERNELS = [
     ("heston_fused_kernelIfLi1ELb0ELb1ELi1ELi10ELi0ELb0E", 5, "f32 Euler, 1 strike (headline)", "fused_f32_1strike_C3"),
     ("heston_fused_kernelIfLi1ELb1ELb1ELi3ELi10ELi0ELb0E", 5, "f32 Euler, strike sweep", "fused_f32_64strikes"),
-    ("heston_fused_kernelIfLi1ELb0ELb1ELb1ELi1ELi10ELi0ELb0E", 5, "f32 Euler, trajectory output", "trajectory_f32_R2000000_N501"),
     ("heston_fused_kernelIdLi2ELb0ELb1ELi2ELi10ELi0ELb0E", 5, "f64 Euler, 1 strike", "fused_f64_1strike"),
     ("heston_fused_kernelIdLi2ELb1ELb1ELi1ELi10ELi0ELb0E", 5, "f64 Euler, strike sweep", "fused_f64_64strikes_C5_shard"),
     ("heston_conditional_kernelILb0ELb0E", 4, "f32 conditional scheme", None),
@@ -57,7 +56,7 @@ def main():
     text = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
     measured = {}
     try:
-        measured = json.load(open(os.path.join(ROOT, "profiles", "r01_aux_kernels_1gpu.json")))
+        measured = json.load(open(os.path.join(ROOT, "profiles", "r02_aux_kernels_1gpu.json")))
     except OSError:
         pass
     print(f"clock {CLOCK / 1e9:.3f} GHz, {SMSP} sub-partitions; weights: IMAD.WIDE/HI 4, FP64 2, other 1")
