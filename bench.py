@@ -171,18 +171,21 @@ def run_reference(args):
 # --------------------------------------------------------------------------- GPU arm
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  ONE sampler for the
+    whole job (rank 0 watches the GPUs of all ranks): eight concurrent nvidia-smi loops would perturb the launches they
+    are meant to watch."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_indices):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+        self.gpu_indices, self.rows, self.proc = list(gpu_indices), [], None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+            self.proc = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(i) for i in self.gpu_indices),
+                                          f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
@@ -209,8 +212,8 @@ class ClockSampler(threading.Thread):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         busy = [c for c in sm if c > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_min_mhz_under_load": min(busy), "sm_max_mhz": max(smax),
+                "reasons": sorted(reasons), "samples": len(sm), "gpus_watched": len(self.gpu_indices)}
 
 
 def profiled_traffic():
@@ -294,9 +297,13 @@ def run_b200(args):
         nK = pricer.launch(p, R, N_T, [PARAMS["K"]], args.seed, sub)
         sub += 1
     sums, sumsq = pricer.finish(nK)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
+    sampler = None
+    if rank == 0:
+        visible = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        # single node: local rank i runs on the i-th visible GPU (index or UUID; nvidia-smi --id takes both)
+        sampler = ClockSampler([visible[i] if i < len(visible) else i for i in range(world)])
+        sampler.start()
+        time.sleep(0.3)
     barrier()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -334,8 +341,10 @@ def run_b200(args):
     ctx.sync()
     e2e_s = time.perf_counter() - t0
     barrier()
-    sampler.stop()
-    clocks = sampler.summary()
+    clocks = None
+    if sampler is not None:
+        sampler.stop()
+        clocks = sampler.summary()
     dev_ms, e2e_s, cond_ms = max_over_ranks(dev_ms, e2e_s, cond_ms)
 
     # ---- the other BASELINE configs and the invariance of the sharded sum (each device-timed on its own)
