@@ -129,7 +129,7 @@ def run_reference(args):
     arm = CpuArm()
     R = PATHS_PER_GPU
     warmups = 0
-    budget_s = float(os.environ.get("COCOS_B200_CPU_ARM_BUDGET_S", "280"))
+    budget_s = float(os.environ.get("COCOS_B200_CPU_ARM_BUDGET_S", "240"))
     t_begin = time.perf_counter()
     per_step = None
     for w in range(args.warmup):
