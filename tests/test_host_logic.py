@@ -5,6 +5,7 @@ import os
 import numpy as np
 import pytest
 
+from conftest import ROOT
 from cocos_b200.multi_processing import utilities as U
 from cocos_b200.numerics import random as rnd
 
@@ -151,3 +152,32 @@ def test_bundled_nccl_is_found_without_importing_torch():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stderr[-1500:]
+
+
+def test_reference_staging_is_byte_exact_and_tamper_evident(tmp_path, monkeypatch):
+    """oracle/build_ref.py: the staged copy the bench's CPU arm imports is the reference byte for byte (SHA-256
+    manifest), and an edited staged file fails verification."""
+    from oracle import build_ref
+    if not build_ref.source_available():
+        pytest.skip("/root/reference is not mounted here")
+    monkeypatch.setattr(build_ref, "STAGED_ROOT", str(tmp_path / "_ref"))
+    monkeypatch.setattr(build_ref, "MANIFEST", str(tmp_path / "_ref" / "MANIFEST.json"))
+    assert build_ref.stage(verbose=False) and build_ref.verify()
+    staged = tmp_path / "_ref" / "examples" / "stochastic_volatility" / "heston_utilities.py"
+    source = os.path.join(build_ref.SOURCE_ROOT, "examples", "stochastic_volatility", "heston_utilities.py")
+    assert staged.read_bytes() == open(source, "rb").read()
+    assert not (tmp_path / "_ref" / "cocos" / "tests").exists()          # the reference's tests are not staged
+    staged.write_text(staged.read_text() + "\n# edited\n")
+    assert not build_ref.verify()
+    assert build_ref.stage(verbose=False) and build_ref.verify()         # staging again restores the original
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_profile():
+    """bench.py's roofline.traffic is dram read + write bytes per launch from the ncu summary under profiles/."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic, source = bench.profiled_traffic()
+    assert source is not None and source.startswith("profiles/") and os.path.exists(os.path.join(ROOT, source))
+    assert traffic is not None and 0 <= traffic < 10_000_000             # a compute-bound kernel: kilobytes, not gigabytes
