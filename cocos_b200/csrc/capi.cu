@@ -806,7 +806,7 @@ extern "C" CB_API int cb_kde_integrate_box_1d_f32(cb_ctx *c, const float *d_poin
     return CB_OK;
 }
 
-extern "C" CB_API int cb_kde_resample_f32(cb_ctx *c, const float *d_points, const float *d_cumweights_or_null, uint64_t n,
+extern "C" CB_API int cb_kde_resample_f32(cb_ctx *c, const float *d_points, const double *d_cumweights_or_null, uint64_t n,
                                           int d, const float *h_chol, uint64_t size, uint64_t seed, uint32_t subsequence,
                                           float *d_out) {
     CB_CTX(c);

@@ -154,7 +154,7 @@ kde_box_1d_kernel(const float *__restrict__ pts, const float *__restrict__ wts, 
 // weights -- words 0 and 1 give the Box-Muller pair for dimensions 0 and 1; a second block (block = 1) of the same
 // counter feeds dimensions 2 and 3.  Output is (d, size) row-major like the reference's.
 __global__ void __launch_bounds__(256)
-kde_resample_kernel(const float *__restrict__ pts /* (n, d) */, const float *__restrict__ cumw /* (n) or NULL */,
+kde_resample_kernel(const float *__restrict__ pts /* (n, d) */, const double *__restrict__ cumw /* (n) or NULL */,
                     uint64_t n, int d, const float *__restrict__ chol /* d x d lower, row-major */, uint64_t size,
                     const __grid_constant__ PhiloxKeys k, uint32_t subseq, float *__restrict__ out /* (d, size) */) {
     __shared__ float s_l[16];
@@ -163,14 +163,14 @@ kde_resample_kernel(const float *__restrict__ pts /* (n, d) */, const float *__r
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < size; s += stride) {
         const uint4 o = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), 0u, subseq, k);
-        // data point: 32 + 23 bits of uniform so that n up to 2^40 is resolved
+        // data point: 32 + 23 bits of uniform (double), so that large n and small weights are resolved
+        const double u01 = ((double)o.w + (double)(o.z >> 9) * (1.0 / 8388608.0)) * (1.0 / 4294967296.0);   // [0,1)
         uint64_t idx;
         if (cumw == nullptr) {
-            const double u = ((double)o.w + (double)(o.z >> 9) * (1.0 / 8388608.0)) * (1.0 / 4294967296.0);   // [0,1)
-            idx = (uint64_t)(u * (double)n);
+            idx = (uint64_t)(u01 * (double)n);
             if (idx >= n) idx = n - 1;
         } else {
-            const float u = u01_f32(o.w) * cumw[n - 1];
+            const double u = u01 * cumw[n - 1];
             uint64_t lo = 0, hi = n - 1;                       // first i with cumw[i] > u
             while (lo < hi) {
                 const uint64_t mid = (lo + hi) >> 1;
@@ -203,7 +203,7 @@ cudaError_t launch_kde_box_1d(const float *d_pts, const float *d_w, uint64_t n, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_kde_resample(const float *d_pts, const float *d_cumw, uint64_t n, int d, const float *d_chol,
+cudaError_t launch_kde_resample(const float *d_pts, const double *d_cumw, uint64_t n, int d, const float *d_chol,
                                 uint64_t size, const PhiloxKeys &k, uint32_t subseq, float *d_out, cudaStream_t s) {
     if (size == 0) return cudaSuccess;
     uint64_t b = (size + 255) / 256;

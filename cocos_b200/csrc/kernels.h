@@ -149,7 +149,7 @@ cudaError_t launch_kde_moments(const float *d_pts, const float *d_w, uint64_t n,
 cudaError_t launch_kde_whiten(const float *d_in, uint64_t n, int d, const float *d_W, float *d_out, cudaStream_t s);
 cudaError_t launch_kde_box_1d(const float *d_pts, const float *d_w, uint64_t n, double low, double high, double sd,
                               double *d_out, cudaStream_t s);
-cudaError_t launch_kde_resample(const float *d_pts, const float *d_cumw, uint64_t n, int d, const float *d_chol,
+cudaError_t launch_kde_resample(const float *d_pts, const double *d_cumw, uint64_t n, int d, const float *d_chol,
                                 uint64_t size, const PhiloxKeys &k, uint32_t subseq, float *d_out, cudaStream_t s);
 int kde_plan_chunks(uint64_t n, uint64_t m, int sm_count, int *pj_out);
 cudaError_t launch_kde_evaluate(const float *d_p, const float *d_w, uint64_t n, int d, const float *d_q, uint64_t m,

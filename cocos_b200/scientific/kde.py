@@ -283,8 +283,8 @@ class gaussian_kde:
             raise TypeError("seed must be None or an integer (the device generator is Philox4x32-10)")
         ctx = self._ctx
         if self._weights is not None and getattr(self, "_cumweights_dev", None) is None:
-            cum = np.cumsum(self._weights.astype(np.float64)).astype(np.float32)
-            self._cumweights_dev = empty_on(ctx, (self.n,), np.float32)
+            cum = np.cumsum(self._weights.astype(np.float64))
+            self._cumweights_dev = empty_on(ctx, (self.n,), np.float64)
             _lib.check(_lib.lib().cb_memcpy_h2d(ctx.handle, self._cumweights_dev.data_ptr, cum.ctypes.data, cum.nbytes))
         chol = np.ascontiguousarray(np.linalg.cholesky(self.covariance), dtype=np.float32)
         out = empty_on(ctx, (self.d, size), np.float32)

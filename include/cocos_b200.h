@@ -158,9 +158,9 @@ CB_API int cb_kde_evaluate_f32(cb_ctx *ctx, const float *d_wpoints, const float 
 CB_API int cb_kde_integrate_box_1d_f32(cb_ctx *ctx, const float *d_points, const float *d_weights_or_null, uint64_t n,
                                        double low, double high, double stdev, double *h_out);
 /* resample (kde.py:987-1025): d_out (d, size) row-major = dataset[:, index] + chol @ z with index drawn from the
- * weights (d_cumweights = inclusive cumulative sums, NULL = uniform) and z ~ N(0, I); h_chol = LOWER Cholesky factor
+ * weights (d_cumweights = inclusive cumulative sums in double, NULL = uniform) and z ~ N(0, I); h_chol = LOWER Cholesky factor
  * of the kernel covariance (host, row-major d x d); one Philox block per sample */
-CB_API int cb_kde_resample_f32(cb_ctx *ctx, const float *d_points, const float *d_cumweights_or_null, uint64_t n, int d,
+CB_API int cb_kde_resample_f32(cb_ctx *ctx, const float *d_points, const double *d_cumweights_or_null, uint64_t n, int d,
                                const float *h_chol, uint64_t size, uint64_t seed, uint32_t subsequence, float *d_out);
 
 /* ---- Heston paths ---------------------------------------------------------
