@@ -25,7 +25,14 @@
 
 namespace cb {
 
-constexpr int kStage = 6;          // steps per stage = two Philox blocks (three steps each)
+#ifndef CB_TRAJ_STAGE
+#define CB_TRAJ_STAGE 6
+#endif
+#ifndef CB_TRAJ_MINB
+#define CB_TRAJ_MINB 1
+#endif
+constexpr int kStage = CB_TRAJ_STAGE;   // steps per stage: a multiple of three (one Philox block feeds three steps)
+static_assert(kStage % 3 == 0, "a stage is a whole number of Philox blocks");
 constexpr int kTrajThreads = 256;  // fixed block size: stage offsets are immediates, a row segment is 1 KiB (float)
 
 __device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
@@ -39,7 +46,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // WITH_V: also materialise the variance; BULK: TMA bulk stores from a shared-memory stage (else direct STG)
 template <typename real, bool WITH_V, bool MULTI, bool BULK>
-__global__ void __launch_bounds__(kTrajThreads)
+__global__ void __launch_bounds__(kTrajThreads, CB_TRAJ_MINB)
 heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace ws, real *__restrict__ x_out,
                          real *__restrict__ v_out, real *__restrict__ traj_x, real *__restrict__ traj_v) {
     constexpr int NARR = WITH_V ? 4 : 2;                  // staged arrays per step: x1, x2 (, v1, v2)
@@ -147,7 +154,7 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWork
         uint64_t m1b = 0;
         for (uint32_t t = 0; t < trips; ++t) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < kStage / 3; ++h) {
                 StepDraw d0, d1, d2;
                 m1b += kPhiloxM1;
                 const uint4 nxt = rng.block_from_product(m1b, keys);
@@ -164,7 +171,7 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWork
         }
         if (rest) {                                         // 1..5 steps left: uniform across the block
             uint32_t done = 0;
-            for (int h = 0; h < 2 && done < rest; ++h) {
+            for (int h = 0; h < kStage / 3 && done < rest; ++h) {
                 StepDraw d[3];
                 m1b += kPhiloxM1;
                 const uint4 nxt = rng.block_from_product(m1b, keys);
