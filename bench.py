@@ -304,16 +304,23 @@ def run_b200(args):
         sampler = ClockSampler([visible[i] if i < len(visible) else i for i in range(world)])
         sampler.start()
         time.sleep(0.3)
+    # The K timed steps are ENQUEUED on the kernel's stream -- L2 flush, start event, launch (the cross-GPU sum inside),
+    # stop event, K times -- between a barrier + synchronize on both sides; the host is not in the loop, so the launch
+    # skew between the ranks' processes is paid once, not once per step.  Each step is timed by its own pair of CUDA
+    # events recorded on that stream, right around the kernel.
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=torch.device("cuda", local_rank))
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        flush.zero_()                                     # L2 flush between timed steps (untimed)
-        torch.cuda.synchronize()
-        ctx.timer_start()
-        nK = pricer.launch(p, R, N_T, [PARAMS["K"]], args.seed, sub)
-        dev_ms += ctx.timer_stop()
-        sub += 1
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            flush.zero_()                                 # L2 flush between timed steps (untimed, same stream)
+            starts[i].record(stream)
+            nK = pricer.launch(p, R, N_T, [PARAMS["K"]], args.seed, sub)
+            stops[i].record(stream)
+            sub += 1
     barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
     sums, sumsq = pricer.finish(nK)
     price, se = heston._price_from_sums(PARAMS["r"], PARAMS["T"], R, sums, sumsq)
 
@@ -466,6 +473,8 @@ def run_b200(args):
                        "collective": ("none" if world == 1 else
                                       "fused-peer-exchange" if pricer.peer_exchange else "nccl-allreduce"),
                        "l2": "256 MiB memset between timed steps (the kernel itself reads no memory input)",
+                       "timing": "one pair of CUDA events per step on the kernel's stream; the K steps (flush, event, "
+                                 "launch, event) are enqueued between a barrier + synchronize on both sides",
                        "launch": {"threads": args.threads or 256, "blocks_per_sm": args.blocks_per_sm or "max resident",
                                   "pairs_per_thread": args.ppt or 1}},
             "price": float(price[0]), "price_se": float(se[0]),
