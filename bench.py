@@ -171,20 +171,68 @@ def run_reference(args):
 # --------------------------------------------------------------------------- GPU arm
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  ONE sampler for the
-    whole job (rank 0 watches the GPUs of all ranks): eight concurrent nvidia-smi loops would perturb the launches they
-    are meant to watch."""
+    """SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  ONE sampler for the whole
+    job (rank 0 watches the GPUs of all ranks).  The timed region of the default run is short (20 steps x 3.8 ms), so
+    the sampler polls NVML in-process every 5 ms -- the same counters `nvidia-smi --query-gpu=clocks.sm,
+    clocks_event_reasons.*` prints; a 100 ms nvidia-smi loop would catch one sample of it -- and falls back to that
+    nvidia-smi loop where NVML cannot be loaded."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_indices):
+    def __init__(self, gpu_ids):
         super().__init__(daemon=True)
-        self.gpu_indices, self.rows, self.proc = list(gpu_indices), [], None
+        self.gpu_ids, self.rows, self.proc = list(gpu_ids), [], None
+        self._stop_flag = threading.Event()
+        self.source = None
+
+    def _nvml_handles(self):
+        import pynvml
+        pynvml.nvmlInit()
+        handles = []
+        for g in self.gpu_ids:
+            if isinstance(g, str) and not g.strip().isdigit():
+                try:
+                    handles.append(pynvml.nvmlDeviceGetHandleByUUID(g.strip()))
+                except TypeError:
+                    handles.append(pynvml.nvmlDeviceGetHandleByUUID(g.strip().encode()))
+            else:
+                handles.append(pynvml.nvmlDeviceGetHandleByIndex(int(g)))
+        return pynvml, handles
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(i) for i in self.gpu_indices),
+            nv, handles = self._nvml_handles()
+        except Exception:       # noqa: BLE001  (no NVML: the nvidia-smi loop)
+            return self._run_nvidia_smi()
+        self.source = "nvml, 5 ms"
+        bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                 else nv.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0))),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0))),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                         getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0))))
+        try:
+            smax = [nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM) for h in handles]
+            while not self._stop_flag.is_set():
+                for i, h in enumerate(handles):
+                    clock = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:       # noqa: BLE001
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append([str(i), str(clock), str(smax[i]), ""] +
+                                     ["Active" if (bit and mask & bit) else "Not Active" for _, bit in bits])
+                time.sleep(0.005)
+        except Exception:       # noqa: BLE001
+            pass
+
+    def _run_nvidia_smi(self):
+        self.source = "nvidia-smi -lms 100"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(i) for i in self.gpu_ids),
                                           f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -194,6 +242,7 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self._stop_flag.set()
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
@@ -210,10 +259,10 @@ class ClockSampler(threading.Thread):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         busy = [c for c in sm if c > 0.5 * max(sm)] or sm
         return {"sm_mhz": statistics.median(busy), "sm_min_mhz_under_load": min(busy), "sm_max_mhz": max(smax),
-                "reasons": sorted(reasons), "samples": len(sm), "gpus_watched": len(self.gpu_indices)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus_watched": len(self.gpu_ids), "source": self.source}
 
 
 def profiled_traffic():
