@@ -5,6 +5,7 @@ Same names, arguments and return types as the reference:
   compute_option_price_from_simulated_paths     heston_utilities.py:99-119
   simulate_and_compute_option_price             heston_utilities.py:122-164   (the map function)
   simulate_and_compute_option_price_gpu         heston_utilities.py:217-270
+  simulate_and_compute_option_price_multicore   heston_utilities.py:167-214   (same estimator, one fused launch)
 plus what the fused kernel gives for free: standard errors from antithetic pair
 averages, a strike sweep over shared paths (BASELINE config 5), float64 state and the
 full log-price trajectory.  The reference's Python time loop (N-1 iterations of ~21
@@ -211,6 +212,27 @@ def simulate_and_compute_option_price_gpu(
     sums, _ = heston_payoff_sums(x0, v0, r, rho, sigma_v, kappa, v_bar, T, nT, total, [K],
                                  compute_device_pool=compute_device_pool)
     return float(math.exp(-r * T) * sums[0] / total)
+
+
+def simulate_and_compute_option_price_multicore(
+        x0: float, v0: float, r: float, rho: float, sigma_v: float, kappa: float, v_bar: float, T: float, K: float,
+        nT: int, R: int, numerical_package_bundle: tp.Optional[tp.Type[NumericalPackageBundle]] = B200Bundle,
+        number_of_cores: tp.Optional[int] = None) -> float:
+    """The reference's CPU multi-core entry (heston_utilities.py:167-214) maps ``simulate_and_compute_option_price``
+    on its NumPy bundle over ``number_of_cores`` (default ``5 * cpu_count()``) batches of ``ceil(R / number_of_cores)``
+    paths and averages the batch prices.  There is no CPU branch here (a NumPy bundle is refused like everywhere
+    else); with the B200 bundle the same estimator -- ``number_of_cores * ceil(R / number_of_cores)`` paths in all --
+    runs as ONE fused launch, which is what the batches were a workaround for."""
+    _require_b200(numerical_package_bundle)
+    if number_of_cores is None:
+        import multiprocessing
+        number_of_cores = 5 * multiprocessing.cpu_count()
+    number_of_cores = int(number_of_cores)
+    if number_of_cores < 1:
+        raise ValueError("number_of_cores must be at least 1")
+    total = math.ceil(int(R) / number_of_cores) * number_of_cores
+    return simulate_and_compute_option_price(x0=x0, v0=v0, r=r, rho=rho, sigma_v=sigma_v, kappa=kappa, v_bar=v_bar,
+                                             T=T, K=K, nT=nT, R=total)
 
 
 PAYOFF_KINDS = {"european": 0, "asian": 1, "up_and_out": 2, "down_and_out": 3}

@@ -300,3 +300,23 @@ def test_tiny_and_degenerate_shapes(ctx, P):
     odd = fused(ctx, P, 3, 4, [0.95], seed=1, sub=1, outputs=True)
     xm, _ = model(P, 3, 4, 1, 1, np.float32)
     np.testing.assert_allclose(odd[2][:3], xm, atol=1e-5)
+
+
+def test_multicore_entry_point_is_one_fused_launch(gpu_device, golden_values, ref_params):
+    """simulate_and_compute_option_price_multicore (heston_utilities.py:167-214): same signature, same estimator
+    (number_of_cores * ceil(R / number_of_cores) paths), no CPU branch."""
+    from cocos_b200 import heston
+    from cocos_b200.numerics import random as rnd
+    from cocos_b200.numerics.numerical_package_bundle import NumericalPackageBundle
+    rnd.seed(77)
+    price = heston.simulate_and_compute_option_price_multicore(nT=501, R=1_999_999, number_of_cores=7, **ref_params)
+    rnd.seed(77)
+    same = heston.simulate_and_compute_option_price(nT=501, R=math.ceil(1_999_999 / 7) * 7, **ref_params)
+    assert price == same
+    ref = golden_values["statistical"]["nT501"]
+    assert abs(price - ref["price"]) <= 3 * math.hypot(ref["se"], ref["se"] / 1.4)
+
+    class NumpyLike(NumericalPackageBundle):
+        pass
+    with pytest.raises(TypeError):
+        heston.simulate_and_compute_option_price_multicore(nT=11, R=100, numerical_package_bundle=NumpyLike, **ref_params)
