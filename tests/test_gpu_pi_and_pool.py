@@ -168,3 +168,36 @@ def test_array_roundtrip(gpu_device):
     assert f.dtype == np.float32 and np.array_equal(f.to_numpy(), a.astype(np.float32))
     assert cn.array([1.0, 2.0]).dtype == np.float32 and len(cn.array([1.0, 2.0])) == 2
     assert float(cn.array(np.float32(2.5))) == 2.5
+
+
+def test_pi_window_across_the_32_bit_block_boundary(ctx):
+    """Draw windows whose Philox block indices straddle 2^32 (the kernel cuts the index range into segments with a
+    uniform high counter word): the count equals the one computed on the host from the raw Philox words of the same
+    blocks (cb_philox_words), for plain and antithetic points, and windows add up across the boundary."""
+    from cocos_b200 import _lib
+    from cocos_b200.numerics._array import empty_on
+    n = 1 << 36                                      # 6.9e10 points: only windows of it are evaluated
+    seed, sub = 29, 6
+    boundary_draw = 2 * (1 << 32)                    # first draw of block 2^32
+    lo, hi = boundary_draw - 1001, boundary_draw + 1503
+    for antithetic in (False, True):
+        got = pi_count(ctx, n, seed, sub, antithetic, first=lo, count=hi - lo)
+        a = pi_count(ctx, n, seed, sub, antithetic, first=lo, count=boundary_draw - 3 - lo)
+        b = pi_count(ctx, n, seed, sub, antithetic, first=boundary_draw - 3, count=hi - (boundary_draw - 3))
+        assert a + b == got
+        # host evaluation from the raw words of blocks [lo//2, (hi+1)//2)
+        b0, b1 = lo // 2, (hi + 1) // 2
+        words = empty_on(ctx, (b1 - b0, 4), np.uint32)
+        _lib.check(_lib.lib().cb_philox_words(ctx.handle, words.data_ptr, b1 - b0, b0, 0, seed, sub))
+        w = words.to_numpy()
+        u = ((w >> np.uint32(9)).astype(np.uint32) + np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+        ux = u[:, [0, 2]].reshape(-1)                 # draw 2b+h uses words (2h, 2h+1) of block b
+        uy = u[:, [1, 3]].reshape(-1)
+        j = np.arange(2 * b0, 2 * b1)
+        own = (j >= lo) & (j < hi)
+        inside = (ux * ux + uy * uy) <= np.float32(1.0)
+        expect = int(np.count_nonzero(inside & own))
+        if antithetic:
+            rx, ry = np.float32(1.0) - ux, np.float32(1.0) - uy
+            expect += int(np.count_nonzero(((rx * rx + ry * ry) <= np.float32(1.0)) & own & (j < n // 2)))
+        assert got == expect
