@@ -587,7 +587,26 @@ def _extras_single_gpu(ctx, L, p, mufu_peak, peak):
                                       PARAMS["sigma_v"], PARAMS["rho"], PARAMS["x0"], PARAMS["v0"])
     xg, vg = dx.to_numpy(), dv.to_numpy()
     rel = float(np.max(np.abs(np.exp(xg.astype(np.float64)) - np.exp(xo.astype(np.float64))) / np.exp(xo.astype(np.float64))))
+    # ... and, where the staged reference travelled with the repo, with the UNMODIFIED reference itself run live on this
+    # host with the same normals injected into numpy.random.randn (north_star check 1: 1e-6 relative on S_T)
+    live = None
+    try:
+        from oracle import reference_runner as rr
+        if rr.reference_available():
+            ref = rr.load_reference()
+            with rr.InjectedNormals(normals=[Z[s_].astype(np.float64) for s_ in range(N1 - 1)]):
+                xr, vr = ref.simulate_heston_model(T=PARAMS["T"], N=N1, R=R1, mu=PARAMS["r"], kappa=PARAMS["kappa"],
+                                                   v_bar=PARAMS["v_bar"], sigma_v=PARAMS["sigma_v"], rho=PARAMS["rho"],
+                                                   x0=PARAMS["x0"], v0=PARAMS["v0"],
+                                                   numerical_package_bundle=ref.NumpyBundle)
+            xr = np.asarray(xr)
+            live = {"max_rel_err_in_S_T": float(np.max(np.abs(np.exp(xg.astype(np.float64)) - np.exp(xr.astype(np.float64)))
+                                                       / np.exp(xr.astype(np.float64)))),
+                    "bit_identical_x": bool(np.array_equal(xg, xr)), "bit_identical_v": bool(np.array_equal(vg, np.asarray(vr)))}
+    except Exception as exc:      # noqa: BLE001  (the check is a bonus; the oracle comparison below is the gate)
+        live = {"error": repr(exc)[:200]}
     out["C1"] = {"workload": "C1 Heston 100k paths x 100 steps f32, injected normals (parity kernel)", "ms": ms,
+                 "vs_unmodified_reference_live": live,
                  "path_steps_per_s": R1 * (N1 - 1) / ms * 1e3, "GBs_read": Z.nbytes / ms / 1e6,
                  "bit_identical_to_oracle": bool(np.array_equal(xg, xo) and np.array_equal(vg, vo)),
                  "max_rel_err_in_S_T": rel, "parity": bool(rel <= 1e-6),
