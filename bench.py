@@ -546,6 +546,9 @@ def run_b200(args):
             "extras": extras,
         }
         if cpu is not None:
+            # north_star check 2, live: the fused kernel's price against the reference's own NumPy price of the same
+            # configuration (same path count, so the same standard error on both sides)
+            cpu["gpu_price_within_3se"] = bool(abs(float(price[0]) - cpu["price"]) <= 3 * math.sqrt(2.0) * float(se[0]))
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     pricer.close()
