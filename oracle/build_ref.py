@@ -73,6 +73,12 @@ def stage(verbose=True):
         manifest[rel] = digest
     with open(MANIFEST, "w") as fh:
         json.dump({"source": SOURCE_ROOT, "files": manifest}, fh, indent=1, sort_keys=True)
+    with open(os.path.join(STAGED_ROOT, "README.txt"), "w") as fh:
+        fh.write("Byte-for-byte staged copy of the reference (michaelnowotny/cocos: the cocos package and the examples\n"
+                 "tree), written by oracle/build_ref.py from /root/reference for ONE purpose: bench.py's CPU arm imports\n"
+                 "and times the reference's own, unmodified NumPy path on the GPU box, where /root/reference does not\n"
+                 "exist.  This directory is git-ignored: it is not part of the repository and nothing of it is product\n"
+                 "code.  MANIFEST.json holds the SHA-256 of every file; `python oracle/build_ref.py --verify` checks it.\n")
     if verbose:
         print(f"build_ref: staged {len(manifest)} reference files under {STAGED_ROOT}")
     return True
