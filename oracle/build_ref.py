@@ -8,11 +8,14 @@ gpurun-ignored, like the built ``.so`` files).  ``bench.py --impl reference`` an
 (examples/stochastic_volatility/heston_utilities.py:122-164) on its NumPy bundle,
 imported from ``oracle/_ref`` under the stubs of ``oracle/reference_runner.py``.
 
-What is staged: the ``cocos`` package (pure Python, 0.6 MB) and the ``examples`` tree
-(the Heston and pi examples live there, outside the installable package -- which is
-why ``pip install --target`` alone would not do).  Tests, notebooks and images are
-not staged.  A manifest with the SHA-256 of every staged file is written next to
-them; ``verify()`` recomputes it, so a staged copy that was edited is detected.
+What is staged: exactly the reference files that importing its Heston entry point on
+the NumPy bundle loads (24 pure-Python files: the ``cocos`` package's import closure and
+``examples/stochastic_volatility/heston_utilities.py`` -- the examples live outside the
+installable package, which is why ``pip install --target`` alone would not do); the
+closure is determined at staging time by importing the reference in a subprocess.
+Tests, notebooks, images and unrelated modules are not staged.  A manifest with the
+SHA-256 of every staged file is written next to them; ``verify()`` recomputes it, so a
+staged copy that was edited is detected.
 
     python oracle/build_ref.py            # stage (idempotent)
     python oracle/build_ref.py --verify   # check the staged copy against its manifest
@@ -27,8 +30,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCE_ROOT = "/root/reference"
 STAGED_ROOT = os.path.join(HERE, "_ref")
 MANIFEST = os.path.join(STAGED_ROOT, "MANIFEST.json")
-_TREES = ("cocos", "examples")
-_SKIP_DIRS = {"tests", "__pycache__"}
 
 
 def _sha256(path):
@@ -40,12 +41,20 @@ def _sha256(path):
 
 
 def _python_files(root):
-    for tree in _TREES:
-        for base, dirs, files in os.walk(os.path.join(root, tree)):
-            dirs[:] = sorted(d for d in dirs if d not in _SKIP_DIRS)
-            for name in sorted(files):
-                if name.endswith(".py"):
-                    yield os.path.relpath(os.path.join(base, name), root)
+    """Relative paths of the reference files its NumPy Heston path imports (found by importing it in a subprocess
+    under the stubs of reference_runner and listing the modules that were loaded from `root`)."""
+    import subprocess
+    code = ("import os, sys\n"
+            f"sys.path.insert(0, {os.path.dirname(HERE)!r})\n"
+            "from oracle import reference_runner as rr\n"
+            f"rr.REFERENCE_ROOT = {root!r}\n"
+            "rr.load_reference()\n"
+            f"root = {root!r} + os.sep\n"
+            "files = {os.path.relpath(m.__file__, root) for m in list(sys.modules.values())\n"
+            "         if getattr(m, '__file__', None) and m.__file__.startswith(root)}\n"
+            "print('\\n'.join(sorted(files)))\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout
+    return [line.strip() for line in out.splitlines() if line.strip().endswith(".py")]
 
 
 def source_available():
@@ -64,6 +73,8 @@ def stage(verbose=True):
                   f"({'present' if staged_available() else 'nothing'})")
         return staged_available()
     manifest = {}
+    if os.path.isdir(STAGED_ROOT):
+        shutil.rmtree(STAGED_ROOT)                      # never keep files of an earlier, wider staging
     for rel in _python_files(SOURCE_ROOT):
         src, dst = os.path.join(SOURCE_ROOT, rel), os.path.join(STAGED_ROOT, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
