@@ -84,3 +84,27 @@ def test_product_does_not_import_torch():
             "print('ok')\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_plain_c_caller_links_against_the_abi(tmp_path):
+    """examples/c/heston_price.c: a C program (no Python, no C++) compiles against include/cocos_b200.h and links
+    against libcocos_b200.so; without a GPU it fails loudly with the library's own error message (no CPU fallback)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "heston_price"
+    lib_dir = os.path.join(ROOT, "cocos_b200")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-std=c11", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c", "heston_price.c"), "-L", lib_dir, "-lcocos_b200",
+                           f"-Wl,-rpath,{lib_dir}", "-lm", "-o", str(exe)])
+    out = subprocess.run([str(exe), "1000", "11"], capture_output=True, text=True, timeout=120)
+    try:
+        import ctypes
+        have_gpu = ctypes.CDLL("libcuda.so.1").cuInit(0) == 0
+    except OSError:
+        have_gpu = False
+    if have_gpu:
+        assert out.returncode == 0 and "price" in out.stdout, out.stderr
+    else:
+        assert out.returncode != 0 and "no CPU fallback" in out.stderr
