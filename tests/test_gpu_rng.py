@@ -139,3 +139,40 @@ def test_antithetic_errors(cn):
         cn.random.randn_antithetic((4, 2), 0, num_pack=np)
     with pytest.raises(TypeError):
         cn.random.randn(4, dtype=np.int32)
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 70_001])
+def test_fills_into_unaligned_output_write_the_same_elements(cn, n):
+    """The vectorised fast paths need a 16-byte aligned output; a pointer that is only element-aligned (a view into a
+    larger buffer) takes the scalar-store kernels and must produce the same elements, neighbours untouched."""
+    import ctypes
+    from cocos_b200 import _lib
+    from cocos_b200.device import current_context
+    from cocos_b200.numerics._array import empty_on
+    from oracle import philox_numpy as px
+    ctx = current_context()
+    L = _lib.lib()
+    for sfx, dtype, model in (("rand_f32", np.float32, px.rand_f32), ("rand_f64", np.float64, px.rand_f64)):
+        item = np.dtype(dtype).itemsize
+        buf = cn.array(np.full(n + 2, -7.0, dtype=dtype))
+        _lib.check(getattr(L, "cb_" + sfx)(ctx.handle, ctypes.c_void_p(buf.data_ptr + item), n, 11, 3))
+        got = buf.to_numpy()
+        assert got[0] == -7.0 and got[-1] == -7.0
+        assert np.array_equal(got[1:-1], model(n, 11, 3))
+    for sfx, dtype, model, tol in (("randn_f32", np.float32, px.randn_f32_model, None),
+                                   ("randn_f64", np.float64, px.randn_f64_model, 1e-12)):
+        item = np.dtype(dtype).itemsize
+        buf = cn.array(np.full(n + 2, -7.0, dtype=dtype))
+        aligned = empty_on(ctx, (n,), dtype)
+        _lib.check(getattr(L, "cb_" + sfx)(ctx.handle, ctypes.c_void_p(buf.data_ptr + item), n, 11, 3))
+        _lib.check(getattr(L, "cb_" + sfx)(ctx.handle, ctypes.c_void_p(aligned.data_ptr), n, 11, 3))
+        got = buf.to_numpy()
+        assert got[0] == -7.0 and got[-1] == -7.0
+        assert np.array_equal(got[1:-1], aligned.to_numpy())          # same bits as the aligned fast path
+    for kind in (0, 2, 4):                                            # uniform, normal, logistic
+        buf = cn.array(np.full(n + 2, -7.0, dtype=np.float32))
+        aligned = empty_on(ctx, (n,), np.float32)
+        _lib.check(L.cb_random_distribution_f32(ctx.handle, ctypes.c_void_p(buf.data_ptr + 4), n, kind, 0.5, 2.0, 11, 3))
+        _lib.check(L.cb_random_distribution_f32(ctx.handle, ctypes.c_void_p(aligned.data_ptr), n, kind, 0.5, 2.0, 11, 3))
+        got = buf.to_numpy()
+        assert got[0] == -7.0 and got[-1] == -7.0 and np.array_equal(got[1:-1], aligned.to_numpy())
