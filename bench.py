@@ -657,7 +657,7 @@ def _extras_single_gpu(ctx, L, p, mufu_peak, peak):
     last_x = tx[Nt - 1].to_numpy()
     traj["last_row_equals_x_T"] = bool(np.array_equal(last_x, x.to_numpy()))
     traj["hbm_write_peak_GBs"] = hbm_write / 1e9
-    traj["workload"] = f"{Rt} paths x {Nt - 1} steps f32, rows [step][path], TMA bulk stores from a shared-memory stage"
+    traj["workload"] = f"{Rt} paths x {Nt - 1} steps f32, rows [step][path], 2-D TMA tensor stores from a shared-memory stage"
     out["trajectory"] = traj
     return out
 

@@ -12,13 +12,22 @@
 // port of a kernel that is already issue-bound, so they do not go through STG at all:
 //   * every step each thread drops its values into a shared-memory stage with plain STS (conflict-free: consecutive
 //     threads, consecutive words);
-//   * after kStage steps ONE thread of the block hands the stage to the TMA unit: one bulk shared->global copy
-//     (cp.async.bulk, SASS UBLKCP) per row segment of blockDim.x values, i.e. 2 (or 4) instructions per step for
-//     the whole block instead of 2 (or 4) STG + address arithmetic per THREAD and step;
+//   * after kStage steps ONE thread of the block hands the stage to the TMA unit: one 2-D tensor store
+//     (cp.async.bulk.tensor.2d, SASS UTMASTG) per staged ARRAY -- a [kStage rows][blockDim.x columns] box of the
+//     trajectory matrix -- i.e. 2 (or 4) instructions per STAGE for the whole block instead of 2 (or 4) STG +
+//     address arithmetic per THREAD and step.  The issuing thread's serial work between the two halves of the
+//     block barrier is a dozen instructions, so the other warps hardly wait for it.  One tensor map per array and
+//     half ([N][pair_count] with the row pitch of the full matrix): columns beyond the shard's pairs and rows
+//     beyond the last step are clipped by the TMA unit, so ragged tiles and the 1..5 left-over steps need no
+//     special case;
 //   * two stages alternate; a stage is reused only after the bulk group that read it has finished reading
 //     (cp.async.bulk.wait_group.read by the issuing thread, then the block barrier that every flush has anyway).
 // Shards whose rows cannot be cut into 16-byte aligned segments (pair count not a multiple of 16 bytes, or the lone
 // unpaired path of an odd R inside the shard) take the DIRECT variant: predicated, warp-coalesced STG per step.
+#include <cstring>
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "kernels.h"
 #include "heston_step.cuh"
 #include "payoff_reduce.cuh"
@@ -33,10 +42,17 @@ namespace cb {
 #endif
 constexpr int kStage = CB_TRAJ_STAGE;   // steps per stage: a multiple of three (one Philox block feeds three steps)
 static_assert(kStage % 3 == 0, "a stage is a whole number of Philox blocks");
-constexpr int kTrajThreads = 256;  // fixed block size: stage offsets are immediates, a row segment is 1 KiB (float)
+constexpr int kTrajThreads = 256;  // fixed block size: stage offsets are immediates, the box is 256 columns wide
 
-__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
+// tensor maps of one launch: [0] x first halves, [1] x partners, [2] v first halves, [3] v partners
+struct alignas(64) TrajMaps {
+    CUtensorMap m[4];
+};
+
+// smem box [kStage][kTrajThreads] -> rows row.., columns col.. of the mapped matrix (out-of-range parts are clipped)
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap *map, uint32_t col, uint32_t row, uint32_t ssrc) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col),
+                 "r"(row), "r"(ssrc)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -44,14 +60,17 @@ __device__ __forceinline__ void bulk_wait_reads() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// WITH_V: also materialise the variance; BULK: TMA bulk stores from a shared-memory stage (else direct STG)
+// Launch bounds: uncapped registers measured best -- x only: 71 registers / 3 resident blocks 0.403 ms against 0.427 ms
+// at 48 registers / 5 blocks; (x, v) is HBM-bound and within 1% for every cap tried (79 / 64 / 48 registers).
+// WITH_V: also materialise the variance; BULK: TMA tensor stores from a shared-memory stage (else direct STG)
 template <typename real, bool WITH_V, bool MULTI, bool BULK>
 __global__ void __launch_bounds__(kTrajThreads, CB_TRAJ_MINB)
-heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace ws, real *__restrict__ x_out,
-                         real *__restrict__ v_out, real *__restrict__ traj_x, real *__restrict__ traj_v) {
+heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __grid_constant__ TrajMaps maps,
+                         ReduceWorkspace ws, real *__restrict__ x_out, real *__restrict__ v_out,
+                         real *__restrict__ traj_x, real *__restrict__ traj_v) {
     constexpr int NARR = WITH_V ? 4 : 2;                  // staged arrays per step: x1, x2 (, v1, v2)
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    real *stage = reinterpret_cast<real *>(smem_raw);     // [2][kStage][NARR][B]
+    real *stage = reinterpret_cast<real *>(smem_raw);     // [2][NARR][kStage][B]: one dense box per array
     constexpr uint32_t B = kTrajThreads;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t tiles = (c.pair_count + B - 1) / B;
@@ -79,7 +98,6 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWork
         const uint64_t tile = round * gridDim.x + blockIdx.x;
         if (tile >= tiles) break;                          // whole block: uniform, no barrier is skipped by a part of it
         const uint64_t tile_first = tile * B;
-        const uint32_t tile_pairs = (uint32_t)(c.pair_count - tile_first < B ? c.pair_count - tile_first : B);
         const uint64_t local = tile_first + threadIdx.x;
         const bool active = local < c.pair_count;
         const uint64_t gp = c.pair_first + (active ? local : 0);     // idle threads replay pair 0, masked everywhere
@@ -105,9 +123,9 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWork
             real w1, w2;
             if constexpr (WITH_V) { w1 = fmax(u1 * k.inv_c1, c.floor_v); w2 = fmax(u2 * k.inv_c1, c.floor_v); }
             if constexpr (BULK) {
-                mine[(s * NARR + 0) * B] = y1;
-                mine[(s * NARR + 1) * B] = y2;
-                if constexpr (WITH_V) { mine[(s * NARR + 2) * B] = w1; mine[(s * NARR + 3) * B] = w2; }
+                mine[(0 * kStage + s) * B] = y1;
+                mine[(1 * kStage + s) * B] = y2;
+                if constexpr (WITH_V) { mine[(2 * kStage + s) * B] = w1; mine[(3 * kStage + s) * B] = w2; }
             } else {
                 row1 += row_len;
                 row2 += row_len;
@@ -121,25 +139,19 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWork
                 }
             }
         };
-        // hand `n` staged steps to the copy engine and switch stages (every thread of the block calls this)
+        // hand the staged steps to the copy engine and switch stages (every thread of the block calls this); `n` of
+        // the kStage rows are new -- the rows after them lie beyond the last time point and are clipped
         auto flush = [&](uint32_t n) {
             if constexpr (BULK) {
                 fence_async_smem();                              // my STS are visible to the async proxy
                 if (threadIdx.x == 0) bulk_wait_reads();         // the OTHER stage (issued one flush ago) has been read
                 __syncthreads();
                 if (threadIdx.x == 0) {
-                    const uint32_t bytes = tile_pairs * (uint32_t)sizeof(real);
+                    constexpr uint32_t box_bytes = kStage * B * (uint32_t)sizeof(real);
                     const uint32_t src0 = stage_smem + parity * stage_elems * (uint32_t)sizeof(real);
-                    for (uint32_t s = 0; s < n; ++s) {
-                        const uint64_t row = (uint64_t)(flushed + s + 1) * row_len + tile_first;
-                        const uint32_t src = src0 + s * NARR * B * (uint32_t)sizeof(real);
-                        bulk_store(traj_x + row, src, bytes);
-                        bulk_store(traj_x + row + c.pair_count, src + B * (uint32_t)sizeof(real), bytes);
-                        if constexpr (WITH_V) {
-                            bulk_store(traj_v + row, src + 2 * B * (uint32_t)sizeof(real), bytes);
-                            bulk_store(traj_v + row + c.pair_count, src + 3 * B * (uint32_t)sizeof(real), bytes);
-                        }
-                    }
+#pragma unroll
+                    for (int a = 0; a < NARR; ++a)
+                        tensor_store_2d(&maps.m[a], (uint32_t)tile_first, flushed + 1, src0 + a * box_bytes);
                     bulk_commit();
                 }
                 flushed += n;
@@ -223,13 +235,47 @@ static size_t trajectory_smem_bytes(bool with_v, bool bulk) {
     return bulk ? (size_t)2 * kStage * (with_v ? 4 : 2) * kTrajThreads * sizeof(real) : 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime (the library links no libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// one half ([rows][pair_count] columns starting at `base`, row pitch = the full matrix row) as a 2-D tensor with a
+// [kStage][kTrajThreads] box
+template <typename real>
+static cudaError_t encode_half(CUtensorMap *map, real *base, uint64_t pair_count, uint64_t rows) {
+    EncodeTiledFn encode = encode_tiled();
+    if (encode == nullptr) return cudaErrorNotSupported;
+    const cuuint64_t dims[2] = {pair_count, rows};
+    const cuuint64_t strides[1] = {2 * pair_count * sizeof(real)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTrajThreads, (cuuint32_t)kStage};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUtensorMapDataType type = sizeof(real) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const CUresult r = encode(map, type, 2, base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <typename real>
 bool trajectory_bulk_eligible(const FusedConsts<real> &c, const real *d_traj_x, const real *d_traj_v) {
     const bool aligned = (reinterpret_cast<uintptr_t>(d_traj_x) % 16 == 0) &&
                          (d_traj_v == nullptr || reinterpret_cast<uintptr_t>(d_traj_v) % 16 == 0);
     const bool rows_cut = (c.pair_count * sizeof(real)) % 16 == 0;
     const bool all_partnered = c.pair_first + c.pair_count <= c.partnered;   // no lone path of an odd R in this shard
-    return aligned && rows_cut && all_partnered && c.pair_count > 0;
+    const bool coordinates_fit = c.pair_count < (1ull << 31);               // tensor coordinates are 32-bit signed
+    return aligned && rows_cut && all_partnered && coordinates_fit && c.pair_count > 0;
 }
 
 template <typename real>
@@ -254,7 +300,18 @@ cudaError_t launch_heston_trajectory(const FusedConsts<real> &c, int blocks, boo
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    void *args[] = {(void *)&c, (void *)&ws, (void *)&d_x, (void *)&d_v, (void *)&d_traj_x, (void *)&d_traj_v};
+    TrajMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (bulk) {
+        const uint64_t rows = (uint64_t)c.steps + 1;
+        cudaError_t e = encode_half(&maps.m[0], d_traj_x, c.pair_count, rows);
+        if (e == cudaSuccess) e = encode_half(&maps.m[1], d_traj_x + c.pair_count, c.pair_count, rows);
+        if (e == cudaSuccess && with_v) e = encode_half(&maps.m[2], d_traj_v, c.pair_count, rows);
+        if (e == cudaSuccess && with_v) e = encode_half(&maps.m[3], d_traj_v + c.pair_count, c.pair_count, rows);
+        if (e != cudaSuccess) return e;
+    }
+    void *args[] = {(void *)&c,   (void *)&maps,     (void *)&ws,      (void *)&d_x,
+                    (void *)&d_v, (void *)&d_traj_x, (void *)&d_traj_v};
     return cudaLaunchKernel(fn, dim3(blocks), dim3(kTrajThreads), args, smem, stream);
 }
 

@@ -57,7 +57,7 @@ def simulate_heston_model(T: float, N: int, R: int, mu: float, kappa: float, v_b
     With ``return_trajectory`` a third array of shape (N, 2*ceil(R/2)) holds every
     path's log price at every time point (row 0 = x0; the last column of an odd R is unused); with
     ``return_variance_trajectory`` a fourth array of the same shape holds the variances (row 0 = v0) --
-    the path-materialising mode, 8 bytes per path-step written with TMA bulk stores.
+    the path-materialising mode, 8 bytes per path-step written with 2-D TMA tensor stores.
     """
     _require_b200(numerical_package_bundle)
     R, N = int(R), int(N)

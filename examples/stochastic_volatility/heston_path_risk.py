@@ -1,7 +1,7 @@
 """Quantifying risk from whole paths (the "quantifying risk" section of the reference's notebook,
 notebooks/Getting Started.ipynb cells 46-64, taken from terminal values to full trajectories):
 simulate the index level AND its variance at every date (the path-materialising mode of the fused kernel, 8 bytes per
-path-step written with TMA bulk stores), then read value-at-risk, expected shortfall and the worst drawdown off them.
+path-step written with TMA tensor stores), then read value-at-risk, expected shortfall and the worst drawdown off them.
 
 python examples/stochastic_volatility/heston_path_risk.py [paths] [dates]
 """

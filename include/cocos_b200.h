@@ -222,7 +222,7 @@ CB_API int cb_heston_payoff_launch_f64(cb_ctx *ctx, const cb_heston_params *p, u
  * log price x_t of every time point goes to d_traj_x and the variance v_t to d_traj_v (NULL: log prices only, i.e.
  * cb_heston_price_launch's d_traj), each [N][2*pair_count], row t = time point t (row 0 = x0 / v0), columns
  * [first halves | partners] of the shard -- the state simulate_heston_model ping-pongs through
- * (heston_utilities.py:60-64, :85-91), kept instead of overwritten.  The stores are TMA bulk copies from a
+ * (heston_utilities.py:60-64, :85-91), kept instead of overwritten.  The stores are 2-D TMA tensor stores from a
  * shared-memory stage when pair_count*sizeof(real) is a multiple of 16 and the shard holds no unpaired path,
  * warp-coalesced direct stores otherwise.  d_x/d_v (terminal state) may be NULL; sums as in cb_heston_price_launch. */
 CB_API int cb_heston_trajectory_launch_f32(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,

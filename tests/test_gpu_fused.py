@@ -170,7 +170,7 @@ def test_trajectory_mode(ctx, P):
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("R,N", [(8_192, 41), (8_000, 14), (5_000, 8), (4_999, 9), (1_000_000, 5)])
 def test_trajectory_with_variance(ctx, P, dtype, R, N):
-    """(x, v) path-materialising mode: TMA bulk stores (aligned shards) and direct stores (ragged shards) write the
+    """(x, v) path-materialising mode: TMA tensor stores (aligned shards) and direct stores (ragged shards) write the
     same rows; the last rows are the terminal state bit for bit; x rows equal the x-only launch."""
     H = (R + 1) // 2
     s, q, x, v, tx, tv = fused(ctx, P, R, N, [0.95], seed=8, sub=2, dtype=dtype, outputs=True, traj_v=True)

@@ -22,8 +22,9 @@ def sass():
     return subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
 
 
-def _loop(sass, prefix):
-    """Opcodes of the shortest backward-branch loop that contains MUFU in the first kernel whose name starts with prefix."""
+def _loop(sass, prefix, mufu=None):
+    """Opcodes of the shortest backward-branch loop that contains MUFU (exactly `mufu` of them when given) in the
+    first kernel whose name starts with prefix."""
     for f in re.split(r"\n\s*Function : ", sass)[1:]:
         if not f.startswith(prefix):
             continue
@@ -38,7 +39,8 @@ def _loop(sass, prefix):
             if m and int(m.group(1), 16) < addr:
                 j = next(k for k, (a, _) in enumerate(lines) if a == int(m.group(1), 16))
                 body = [re.sub(r"^@!?U?P\d\s+", "", x).split()[0] for _, x in lines[j:i + 1]]
-                if any(o.startswith("MUFU") for o in body) and (best is None or len(body) < len(best)):
+                n_mufu = sum(o.startswith("MUFU") for o in body)
+                if n_mufu and (mufu is None or n_mufu == mufu) and (best is None or len(body) < len(best)):
                     best = body
         return best
     raise AssertionError(f"no kernel {prefix} in the library")
@@ -107,3 +109,21 @@ def test_headline_loop_is_the_measured_schedule(sass):
             "the headline loop was scheduled differently: measure it on a B200 (bench.py) before accepting this build"
         return
     raise AssertionError("headline kernel not found")
+
+
+TRAJ_X = "_ZN2cb24heston_trajectory_kernelIfLb0ELb0ELb1E"
+TRAJ_XV = "_ZN2cb24heston_trajectory_kernelIfLb1ELb0ELb1E"
+
+
+@pytest.mark.parametrize("prefix,sts_per_stage", [(TRAJ_X, 12), (TRAJ_XV, 24)])
+def test_trajectory_loop_stores_go_through_the_tma_unit(sass, prefix, sts_per_stage):
+    """One trip of the path-materialising loop = one stage of six steps: the values are dropped into shared memory
+    (STS), ONE tensor store per staged array hands them to the TMA unit (UTMASTG), nothing is stored with STG."""
+    ops = _loop(sass, prefix, mufu=30)                # the full-stage loop (the left-over steps have their own)
+    assert ops is not None
+    assert sum(o.startswith("STS") for o in ops) == sts_per_stage
+    assert sum(o.startswith("UTMASTG") for o in ops) == sts_per_stage // 6
+    assert sum(o.startswith("BAR") for o in ops) == 1
+    for bad in ("STG", "LDG", "UBLKCP", "LDL", "STL"):
+        assert not any(o.startswith(bad) for o in ops), bad
+    assert len(ops) <= (305 if sts_per_stage == 12 else 352)     # 299 / 347 when written
