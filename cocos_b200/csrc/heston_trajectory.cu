@@ -275,7 +275,7 @@ bool trajectory_bulk_eligible(const FusedConsts<real> &c, const real *d_traj_x, 
     const bool rows_cut = (c.pair_count * sizeof(real)) % 16 == 0;
     const bool all_partnered = c.pair_first + c.pair_count <= c.partnered;   // no lone path of an odd R in this shard
     const bool coordinates_fit = c.pair_count < (1ull << 31);               // tensor coordinates are 32-bit signed
-    return aligned && rows_cut && all_partnered && coordinates_fit && c.pair_count > 0;
+    return aligned && rows_cut && all_partnered && coordinates_fit && c.pair_count > 0 && encode_tiled() != nullptr;
 }
 
 template <typename real>

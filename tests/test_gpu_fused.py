@@ -194,9 +194,10 @@ def test_trajectory_with_variance(ctx, P, dtype, R, N):
         assert abs(m[0] - P["v0"]) < 1e-9 and m[-1] > m[0]
 
 
-def test_trajectory_bulk_equals_direct(ctx, P, monkeypatch):
-    """COCOS_B200_NO_BULK=1 forces the direct-store variant on a shard the TMA variant would take: identical output."""
-    R, N = 65_536, 33
+@pytest.mark.parametrize("R,N", [(65_536, 33), (8, 20), (72, 7), (520, 2), (131_080, 12)])
+def test_trajectory_bulk_equals_direct(ctx, P, monkeypatch, R, N):
+    """COCOS_B200_NO_BULK=1 forces the direct-store variant on a shard the TMA variant would take: identical output
+    (also for shards narrower than the 256-column box, boxes cut by the last column, and fewer steps than a stage)."""
     a = fused(ctx, P, R, N, [0.9, 1.0], seed=9, sub=1, outputs=True, traj_v=True)
     monkeypatch.setenv("COCOS_B200_NO_BULK", "1")
     b = fused(ctx, P, R, N, [0.9, 1.0], seed=9, sub=1, outputs=True, traj_v=True)
