@@ -15,17 +15,21 @@ namespace cb {
 // ---- per-type math ---------------------------------------------------------
 
 __device__ __forceinline__ float root(float v) { return mufu_sqrt(v); }
-// double sqrt without the IEEE fix-up path: MUFU.RSQ64H seed (~2^-22) + ONE Newton step on 1/sqrt folded into the
-// product,  g = p y,  e = 1 - g y,  sqrt p ~ g (1 + e/2)  =>  relative error 3 e^2/8 ~ 2^-45 -- seven orders below the
-// float accuracy of the normals that multiply it (the parity kernel keeps __dsqrt_rn).  FP64 instructions cost two
-// issue cycles each on B200, so the step count matters: 4 FP64 + 1 MUFU, no F2F (conversions share the XU pipe).
-// p > 0 always: euler_pair keeps lg2 U away from zero.
+// double sqrt at the accuracy of everything else that multiplies it: ONE multiply on the MUFU.RSQ64H seed.
+// rsqrt.approx.f64 reads only the HIGH word of p (20 mantissa bits) and is good to ~2^-22 -- the accuracy class of the
+// MUFU lg2/sin/cos that make the normals this root is multiplied with, in the float64 kernel as in the float32 one
+// (the float64 kernel keeps float64 STATE and accumulation; its normals are single-precision grade).
+// Measured on B200 over 1.2e9 operands (tools/rsqrt_seed_error.cu; log-uniform p and the kernel's own p = u*lg2 U give
+// the same figures): relative error of p*seed against sqrt(p): mean -1.3334e-7, rms 2.76e-7, |.| < 1e-6.  The mean
+// is taken out for free by StepRegs<double>, which scales c1 (q = sqrt(u*lg2 U) carries sqrt(c1)) by 1 + 2.6668e-7;
+// what is left is zero-mean noise of the size of the MUFU.SQRT error of the float32 kernel.  FP64 instructions cost
+// two issue cycles each on B200: the Newton step this replaces (3 more FP64 per root, 6 of ~20 per pair-step) bought
+// a 2^-45 root under 2^-22 normals and 9% of the kernel's time.
+// The parity kernel keeps __dsqrt_rn.  p > 0 always: euler_pair keeps lg2 U away from zero.
 __device__ __forceinline__ double root(double p) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-    const double g = p * y;
-    const double e = fma(-g, y, 1.0);
-    return fma(g * 0.5, e, g);
+    return p * y;
 }
 // min without the NaN bookkeeping of fmin(double) (DSETP + 2 SEL instead of 6 instructions)
 __device__ __forceinline__ float floor_min(float a, float b) { return fminf(a, b); }
@@ -46,7 +50,10 @@ struct StepRegs {
     real inv_c1;     // v = u * inv_c1
     float two_pi;
     __device__ __forceinline__ explicit StepRegs(const FusedConsts<real> &c) {
-        const real c1 = (real)c.neg2ln2_dt;
+        // double: c1 = -2 ln2 dt from the double drift (not the float copy); the seed-only root() above is 1.3334e-7
+        // too small on average -> c1 is scaled by 1 + 2 * 1.3334e-7 (q = sqrt(u * lg2 U) carries sqrt(c1))
+        const real c1 = sizeof(real) == 8 ? (real)((double)c.drift_v * (4.0 * 0.6931471805599453) * (1.0 + 2.6668e-7))
+                                          : (real)c.neg2ln2_dt;
         drift_u = c.drift_v / c1;
         decay = c.decay;
         pull_u = c1 * c.pull;

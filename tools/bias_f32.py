@@ -9,6 +9,7 @@ python tools/bias_f32.py [paths_total=1e8] [nT=1001] [oracle_paths=1e6] [out.jso
     exp of the payoff) are compared as well.
 (2) float32 kernel against the oracle's float64 model of the same stream with exact libm Box-Muller
     (oracle/heston_numpy.py: fused_model) -- this also sees the MUFU.LG2 / SIN / COS approximation of the normals.
+(3) float64 kernel against the same exact model (its normals and diffusion root are single-precision grade too).
 Reported: mean difference +- its standard error (paired), in price units (discounted).
 """
 import ctypes
@@ -73,10 +74,21 @@ def against_oracle(ctx, R, nT, seed=7, sub=900):
     t0 = time.perf_counter()
     xm, _ = hn.fused_model(P["x0"], P["v0"], P["r"], P["rho"], P["sigma_v"], P["kappa"], P["v_bar"], P["T"], nT, R,
                            seed=seed, subsequence=sub, dtype=np.float64)
-    d = payoff(x32) - payoff(np.asarray(xm, dtype=np.float64))
-    return {"paths": R, "nT": nT, "mean_payoff_difference_f32_minus_exact_model": disc * float(d.mean()),
-            "standard_error": disc * float(d.std() / math.sqrt(d.size)),
-            "max_abs_x_difference": float(np.max(np.abs(x32 - xm))), "oracle_seconds": time.perf_counter() - t0}
+    seconds = time.perf_counter() - t0
+    xm = np.asarray(xm, dtype=np.float64)
+    d = payoff(x32) - payoff(xm)
+    res = {"paths": R, "nT": nT, "mean_payoff_difference_f32_minus_exact_model": disc * float(d.mean()),
+           "standard_error": disc * float(d.std() / math.sqrt(d.size)),
+           "max_abs_x_difference": float(np.max(np.abs(x32 - xm))), "oracle_seconds": seconds}
+    # (3) the float64 kernel (float64 state, single-precision-grade normals and diffusion root) against the same model
+    x64, _ = terminal(ctx, "f64", np.float64, R, nT, seed, sub)
+    d64 = payoff(x64) - payoff(xm)
+    res["f64_kernel"] = {"mean_payoff_difference_f64_kernel_minus_exact_model": disc * float(d64.mean()),
+                         "standard_error": disc * float(d64.std() / math.sqrt(d64.size)),
+                         "max_abs_x_difference": float(np.max(np.abs(x64 - xm))),
+                         "mean_x_difference": float(np.mean(x64 - xm)),
+                         "mean_abs_x_difference": float(np.mean(np.abs(x64 - xm)))}
+    return res
 
 
 def main():

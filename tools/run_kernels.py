@@ -48,3 +48,11 @@ timed("trajectory x,v", lambda r: _lib.check(L.cb_heston_trajectory_launch_f32(
     ctx.handle, ctypes.byref(HP), R, N, k_arr, nK, 0, r, 0, pairs, None, x.data_ptr, v.data_ptr, tx.data_ptr,
     tv.data_ptr)), R * (N - 1), "path-steps/s")
 ctx.sync()
+del tx, tv
+R, N = 12_500_000, 253                      # one GPU's shard of C5
+s64, n64 = _lib.strikes_array(list(np.linspace(0.8, 1.2, 64)))
+timed("pricing f64, 1 strike", lambda r: _lib.check(L.cb_heston_price_launch_f64(
+    ctx.handle, ctypes.byref(HP), R, N, k_arr, nK, 0, r, 0, R // 2, None, None, None, None)), R * (N - 1), "path-steps/s")
+timed("pricing f64, 64 strikes", lambda r: _lib.check(L.cb_heston_price_launch_f64(
+    ctx.handle, ctypes.byref(HP), R, N, s64, n64, 0, r, 0, R // 2, None, None, None, None)), R * (N - 1), "path-steps/s")
+ctx.sync()
