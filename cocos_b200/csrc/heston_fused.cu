@@ -172,8 +172,9 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
 template <typename real>
 constexpr int kSweepMinBlocks = sizeof(real) == 4 ? 3 : 1;
 
-// double, two pairs per thread, one strike: capped at 128 registers (two 256-thread blocks' worth) four 128-thread
-// blocks are resident instead of three (+2%); the strike sweep spills under the same cap and stays uncapped
+// double, two pairs per thread: capped at 128 registers (two 256-thread blocks' worth) four 128-thread blocks are
+// resident instead of three (+2% for one strike, +4% for the sweep); the strike sweep fits under the cap since its
+// positive parts are d + |d| (122 registers, no spills; it takes 152 uncapped)
 template <typename real>
 constexpr int kTwoPairMinBlocks = sizeof(real) == 8 ? 2 : 1;
 
@@ -184,7 +185,7 @@ constexpr int kExchangePairs = sizeof(real) == 8 ? 2 : 1;
 template <typename real, int PPT, bool MULTI>
 constexpr int default_min_blocks() {
     if (PPT == 1 && MULTI) return kSweepMinBlocks<real>;
-    if (PPT == 2 && !MULTI) return kTwoPairMinBlocks<real>;
+    if (PPT == 2) return kTwoPairMinBlocks<real>;
     return 1;
 }
 
