@@ -87,8 +87,8 @@ heston_fused_kernel(const __grid_constant__ FusedConsts<real> c, ReduceWorkspace
                         f1[q] += exp_real(x1[q] + run_shift);
                         f2[q] += exp_real(x2[q] + run_shift);
                     } else {
-                        f1[q] = fmax(f1[q], c.barrier_sign * (x1[q] + run_shift));
-                        f2[q] = fmax(f2[q], c.barrier_sign * (x2[q] + run_shift));
+                        f1[q] = plain_max(f1[q], c.barrier_sign * (x1[q] + run_shift));
+                        f2[q] = plain_max(f2[q], c.barrier_sign * (x2[q] + run_shift));
                     }
                 }
             }

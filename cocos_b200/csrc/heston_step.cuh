@@ -34,6 +34,9 @@ __device__ __forceinline__ double root(double p) {
 // min without the NaN bookkeeping of fmin(double) (DSETP + 2 SEL instead of 6 instructions)
 __device__ __forceinline__ float floor_min(float a, float b) { return fminf(a, b); }
 __device__ __forceinline__ double floor_min(double a, double b) { return a < b ? a : b; }
+// max without the NaN bookkeeping of fmax(double) (the operands are never NaN here)
+__device__ __forceinline__ float plain_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double plain_max(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ float exp_real(float x) { return mufu_ex2(x * 1.4426950408889634f); }
 __device__ __forceinline__ double exp_real(double x) { return exp(x); }
 

@@ -121,7 +121,7 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __gr
             const real shift = fma(step_f, c.mu_dt, c.x0);       // the drift the loop keeps out of x1/x2
             const real y1 = x1 + shift, y2 = x2 + shift;
             real w1, w2;
-            if constexpr (WITH_V) { w1 = fmax(u1 * k.inv_c1, c.floor_v); w2 = fmax(u2 * k.inv_c1, c.floor_v); }
+            if constexpr (WITH_V) { w1 = plain_max(u1 * k.inv_c1, c.floor_v); w2 = plain_max(u2 * k.inv_c1, c.floor_v); }
             if constexpr (BULK) {
                 mine[(0 * kStage + s) * B] = y1;
                 mine[(1 * kStage + s) * B] = y2;
