@@ -198,6 +198,11 @@ CB_API int cb_heston_terminal_injected_host_f32(cb_ctx *ctx, const float *h_Z, c
  *                 the whole simulation)
  *   d_traj        NULL, or [N][2*pair_count] (same path layout per row): the whole
  *                 log-price trajectory, row 0 = x0 (path-materialising mode)
+ * _f64 keeps the state (x, v), the updates and the payoff sums in double; its normals
+ * and the diffusion square root are single-precision grade like the _f32 kernel's
+ * (MUFU lg2/sin/cos, RSQ64H seed; bias against an exact-libm double model of the same
+ * stream: -6.5e-9 in price units).  Bit-for-bit double arithmetic on
+ * caller-supplied normals is cb_heston_terminal_injected_f64.
  * _launch is asynchronous; _finish synchronises the stream and copies the sums
  * (UNDISCOUNTED: sum of payoffs, sum of squared antithetic-unit averages) out. */
 CB_API int cb_heston_price_launch_f32(cb_ctx *ctx, const cb_heston_params *p, uint64_t R, uint32_t N,
