@@ -98,6 +98,21 @@ __device__ __forceinline__ void split_draws(const uint4 &o, uint32_t one_bits, S
     d2.t_angle = angle_float(__funnelshift_l(o.w << 20, o.z, 14), one_bits);
 }
 
+// float -> double of a NORMAL, strictly NEGATIVE float without F2F: the conversion instruction shares the XU pipe with
+// the MUFUs, and the float64 kernel has 5 MUFU + 2 RSQ64H + 3 F2F per pair-step on it (ncu: XU 75% busy, the busiest
+// pipe).  Re-biasing the exponent with integer arithmetic is exact and costs LEA.HI + SHL: -3.4% kernel time
+// (3.66 -> 3.54 ms on the C5 shard).  Only lg2 U has a known sign; the same for cos and g (sign and zero handling: four
+// integer instructions each) was measured slower (3.75 ms) and is left to F2F.
+template <typename real>
+__device__ __forceinline__ real widen_negative(float f);
+template <>
+__device__ __forceinline__ float widen_negative<float>(float f) { return f; }
+template <>
+__device__ __forceinline__ double widen_negative<double>(float f) {
+    const uint32_t b = __float_as_uint(f);       // 1 | E (8) | M (23)  ->  1 | E + 896 (11) | M << 29 (52)
+    return __hiloint2double((int)((b >> 3) + 0xA8000000u), (int)(b << 29));
+}
+
 // One Euler step of an antithetic pair from one (radius, angle) draw.
 //
 // With r^2 = -2 dt ln U and (c, s) = (cos, sin)(theta) the reference needs sqrt(v)*dB0 = sqrt(v)*r*c and
@@ -110,7 +125,7 @@ __device__ __forceinline__ void euler_pair(real &x1, real &u1, real &x2, real &u
     float L_f = mufu_lg2(2.0f - t_radius);                                // lg2 U <= 0, U in (0,1]
     if constexpr (sizeof(real) == 8) L_f -= 1.17549435e-38f;              // U = 1: keeps the rsqrt seed of root() finite;
                                                                           // every other lg2 U (|.| >= 2^-24) is unchanged
-    const real L = (real)L_f;
+    const real L = widen_negative<real>(L_f);                             // exact; no F2F for double
     const float theta = fmaf(t_angle, k.two_pi, -kThreePi);               // [-pi,pi)
     const float cs_f = mufu_cos(theta), sn_f = mufu_sin(theta);
     const real cs = (real)cs_f;

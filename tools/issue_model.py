@@ -24,7 +24,7 @@ KERNELS = [
     ("heston_fused_kernelIfLi1ELb0ELb1ELi1ELi10ELi0ELb0E", 5, "f32 Euler, 1 strike (headline)", "fused_f32_1strike_C3"),
     ("heston_fused_kernelIfLi1ELb1ELb1ELi3ELi10ELi0ELb0E", 5, "f32 Euler, strike sweep", "fused_f32_64strikes"),
     ("heston_fused_kernelIdLi2ELb0ELb1ELi2ELi10ELi0ELb0E", 5, "f64 Euler, 1 strike", "fused_f64_1strike"),
-    ("heston_fused_kernelIdLi2ELb1ELb1ELi1ELi10ELi0ELb0E", 5, "f64 Euler, strike sweep", "fused_f64_64strikes_C5_shard"),
+    ("heston_fused_kernelIdLi2ELb1ELb1ELi2ELi10ELi0ELb0E", 5, "f64 Euler, strike sweep", "fused_f64_64strikes_C5_shard"),
     ("heston_conditional_kernelILb0ELb0E", 4, "f32 conditional scheme", None),
 ]
 FP64 = {"DFMA", "DMUL", "DADD", "DSETP"}
