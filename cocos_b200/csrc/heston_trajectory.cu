@@ -42,14 +42,19 @@ namespace cb {
 #endif
 constexpr int kStage = CB_TRAJ_STAGE;   // steps per stage: a multiple of three (one Philox block feeds three steps)
 static_assert(kStage % 3 == 0, "a stage is a whole number of Philox blocks");
-constexpr int kTrajThreads = 256;  // fixed block size: stage offsets are immediates, the box is 256 columns wide
+constexpr int kBox = 256;                       // columns of one TMA box (the hardware limit per dimension)
+// Block width (fixed per instantiation: stage offsets are immediates).  The float (x, v) variant is HBM-bound and runs
+// 512 threads wide -- each row segment it writes is 2 KiB instead of 1 KiB, two boxes side by side: 0.526-0.538 ms
+// against 0.553-0.558 ms on the same box (DRAM page locality); everything else is issue-bound and fastest at 256.
+template <typename real, bool WITH_V, bool BULK>
+constexpr int kTrajThreadsOf = (WITH_V && BULK && sizeof(real) == 4) ? 512 : 256;
 
 // tensor maps of one launch: [0] x first halves, [1] x partners, [2] v first halves, [3] v partners
 struct alignas(64) TrajMaps {
     CUtensorMap m[4];
 };
 
-// smem box [kStage][kTrajThreads] -> rows row.., columns col.. of the mapped matrix (out-of-range parts are clipped)
+// smem box [kStage][kBox] -> rows row.., columns col.. of the mapped matrix (out-of-range parts are clipped)
 __device__ __forceinline__ void tensor_store_2d(const CUtensorMap *map, uint32_t col, uint32_t row, uint32_t ssrc) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col),
                  "r"(row), "r"(ssrc)
@@ -64,13 +69,16 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // at 48 registers / 5 blocks; (x, v) is HBM-bound and within 1% for every cap tried (79 / 64 / 48 registers).
 // WITH_V: also materialise the variance; BULK: TMA tensor stores from a shared-memory stage (else direct STG)
 template <typename real, bool WITH_V, bool MULTI, bool BULK>
-__global__ void __launch_bounds__(kTrajThreads, CB_TRAJ_MINB)
+__global__ void __launch_bounds__((kTrajThreadsOf<real, WITH_V, BULK>),
+                                  (kTrajThreadsOf<real, WITH_V, BULK> == 512 ? 2 : CB_TRAJ_MINB))
 heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __grid_constant__ TrajMaps maps,
                          ReduceWorkspace ws, real *__restrict__ x_out, real *__restrict__ v_out,
                          real *__restrict__ traj_x, real *__restrict__ traj_v) {
     constexpr int NARR = WITH_V ? 4 : 2;                  // staged arrays per step: x1, x2 (, v1, v2)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     real *stage = reinterpret_cast<real *>(smem_raw);     // [2][NARR][kStage][B]: one dense box per array
+    constexpr int kTrajThreads = kTrajThreadsOf<real, WITH_V, BULK>;
+    constexpr int kSubs = kTrajThreads / kBox;            // boxes side by side per block and array
     constexpr uint32_t B = kTrajThreads;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t tiles = (c.pair_count + B - 1) / B;
@@ -92,7 +100,8 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __gr
     // the two stages alternate for the whole launch (not per tile): a stage is rewritten only after the flush that
     // waited for its last reader
     uint32_t parity = 0;
-    real *mine = stage + threadIdx.x;                      // this thread's column in the current stage
+    const uint32_t my_col = (threadIdx.x / kBox) * (kStage * kBox) + (threadIdx.x % kBox);
+    real *mine = stage + my_col;                           // this thread's column in the current stage
 
     for (uint64_t round = 0; round < rounds; ++round) {
         const uint64_t tile = round * gridDim.x + blockIdx.x;
@@ -123,9 +132,9 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __gr
             real w1, w2;
             if constexpr (WITH_V) { w1 = plain_max(u1 * k.inv_c1, c.floor_v); w2 = plain_max(u2 * k.inv_c1, c.floor_v); }
             if constexpr (BULK) {
-                mine[(0 * kStage + s) * B] = y1;
-                mine[(1 * kStage + s) * B] = y2;
-                if constexpr (WITH_V) { mine[(2 * kStage + s) * B] = w1; mine[(3 * kStage + s) * B] = w2; }
+                mine[(0 * kSubs * kStage + s) * kBox] = y1;
+                mine[(1 * kSubs * kStage + s) * kBox] = y2;
+                if constexpr (WITH_V) { mine[(2 * kSubs * kStage + s) * kBox] = w1; mine[(3 * kSubs * kStage + s) * kBox] = w2; }
             } else {
                 row1 += row_len;
                 row2 += row_len;
@@ -147,16 +156,19 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __gr
                 if (threadIdx.x == 0) bulk_wait_reads();         // the OTHER stage (issued one flush ago) has been read
                 __syncthreads();
                 if (threadIdx.x == 0) {
-                    constexpr uint32_t box_bytes = kStage * B * (uint32_t)sizeof(real);
+                    constexpr uint32_t box_bytes = kStage * kBox * (uint32_t)sizeof(real);
                     const uint32_t src0 = stage_smem + parity * stage_elems * (uint32_t)sizeof(real);
 #pragma unroll
                     for (int a = 0; a < NARR; ++a)
-                        tensor_store_2d(&maps.m[a], (uint32_t)tile_first, flushed + 1, src0 + a * box_bytes);
+#pragma unroll
+                        for (int sub = 0; sub < kSubs; ++sub)
+                            tensor_store_2d(&maps.m[a], (uint32_t)tile_first + sub * kBox, flushed + 1,
+                                            src0 + (a * kSubs + sub) * box_bytes);
                     bulk_commit();
                 }
                 flushed += n;
                 parity ^= 1u;
-                mine = stage + parity * stage_elems + threadIdx.x;
+                mine = stage + parity * stage_elems + my_col;
             }
         };
 
@@ -213,7 +225,14 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __gr
     if constexpr (BULK) {
         if (threadIdx.x == 0) bulk_wait_all();             // the stage must outlive the copies that read it
     }
-    acc.template publish<true>(c.nK, ws);
+    if constexpr (kTrajThreads > kFusedMaxThreads) {       // wide block: the (now idle) stage holds the per-warp rows
+        static_assert(BULK && sizeof(real) * 2 * kStage * NARR * kTrajThreads >= sizeof(double) * (kTrajThreads / 32) * kMaxAcc,
+                      "the stage is large enough for the reduction rows");
+        __syncthreads();                                   // after thread 0's wait: nobody overwrites a stage in flight
+        acc.template publish<true>(c.nK, ws, reinterpret_cast<double (*)[kMaxAcc]>(smem_raw));
+    } else {
+        acc.template publish<true>(c.nK, ws);
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -231,8 +250,14 @@ static const void *trajectory_fn(bool with_v, bool multi, bool bulk) {
 }
 
 template <typename real>
+static int trajectory_threads(bool with_v, bool bulk) {
+    return with_v ? (bulk ? kTrajThreadsOf<real, true, true> : kTrajThreadsOf<real, true, false>)
+                  : (bulk ? kTrajThreadsOf<real, false, true> : kTrajThreadsOf<real, false, false>);
+}
+
+template <typename real>
 static size_t trajectory_smem_bytes(bool with_v, bool bulk) {
-    return bulk ? (size_t)2 * kStage * (with_v ? 4 : 2) * kTrajThreads * sizeof(real) : 0;
+    return bulk ? (size_t)2 * kStage * (with_v ? 4 : 2) * trajectory_threads<real>(with_v, bulk) * sizeof(real) : 0;
 }
 
 // cuTensorMapEncodeTiled through the runtime (the library links no libcuda)
@@ -252,14 +277,14 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // one half ([rows][pair_count] columns starting at `base`, row pitch = the full matrix row) as a 2-D tensor with a
-// [kStage][kTrajThreads] box
+// [kStage][kBox] box
 template <typename real>
 static cudaError_t encode_half(CUtensorMap *map, real *base, uint64_t pair_count, uint64_t rows) {
     EncodeTiledFn encode = encode_tiled();
     if (encode == nullptr) return cudaErrorNotSupported;
     const cuuint64_t dims[2] = {pair_count, rows};
     const cuuint64_t strides[1] = {2 * pair_count * sizeof(real)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTrajThreads, (cuuint32_t)kStage};
+    const cuuint32_t box[2] = {(cuuint32_t)kBox, (cuuint32_t)kStage};
     const cuuint32_t elem[2] = {1, 1};
     const CUtensorMapDataType type = sizeof(real) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     const CUresult r = encode(map, type, 2, base, dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -282,12 +307,12 @@ template <typename real>
 cudaError_t trajectory_occupancy(bool with_v, bool multi, bool bulk, int *threads, int *blocks_per_sm) {
     const void *fn = trajectory_fn<real>(with_v, multi, bulk);
     const size_t smem = trajectory_smem_bytes<real>(with_v, bulk);
-    *threads = kTrajThreads;
+    *threads = trajectory_threads<real>(with_v, bulk);
     if (smem > 32 * 1024) {   // static shared memory (strikes, reduction scratch) comes on top of the stage
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, kTrajThreads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, *threads, smem);
 }
 
 template <typename real>
@@ -312,7 +337,7 @@ cudaError_t launch_heston_trajectory(const FusedConsts<real> &c, int blocks, boo
     }
     void *args[] = {(void *)&c,   (void *)&maps,     (void *)&ws,      (void *)&d_x,
                     (void *)&d_v, (void *)&d_traj_x, (void *)&d_traj_v};
-    return cudaLaunchKernel(fn, dim3(blocks), dim3(kTrajThreads), args, smem, stream);
+    return cudaLaunchKernel(fn, dim3(blocks), dim3(trajectory_threads<real>(with_v, bulk)), args, smem, stream);
 }
 
 #define CB_INSTANTIATE(real)                                                                                       \

@@ -149,11 +149,14 @@ struct PayoffAccumulator {
     // by every thread of the block.
     // XCHG: the instantiation carries the fused cross-GPU step (kept out of the single-GPU kernels: its mere presence
     // changes ptxas' schedule of the time loop, -0.9% on the headline kernel)
+    // scratch: blocks wider than kFusedMaxThreads (the 512-thread path-materialising kernel) hand in shared memory of
+    // their own for the per-warp rows, [blockDim.x / 32][kMaxAcc] doubles
     template <bool XCHG = false>
-    __device__ __forceinline__ void publish(int nK, ReduceWorkspace ws) const {
+    __device__ __forceinline__ void publish(int nK, ReduceWorkspace ws, double (*scratch)[kMaxAcc] = nullptr) const {
         const int nacc = 2 * nK;
-        __shared__ double s_acc[kFusedMaxWarps][kMaxAcc];
+        __shared__ double s_own[kFusedMaxWarps][kMaxAcc];
         __shared__ bool s_last;
+        double (*s_acc)[kMaxAcc] = scratch != nullptr ? scratch : s_own;
         const unsigned lane = threadIdx.x & 31;
         const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
         if constexpr (!MULTI) {
