@@ -13,13 +13,13 @@
 //   * every step each thread drops its values into a shared-memory stage with plain STS (conflict-free: consecutive
 //     threads, consecutive words);
 //   * after kStage steps ONE thread of the block hands the stage to the TMA unit: one 2-D tensor store
-//     (cp.async.bulk.tensor.2d, SASS UTMASTG) per staged ARRAY -- a [kStage rows][blockDim.x columns] box of the
-//     trajectory matrix -- i.e. 2 (or 4) instructions per STAGE for the whole block instead of 2 (or 4) STG +
-//     address arithmetic per THREAD and step.  The issuing thread's serial work between the two halves of the
-//     block barrier is a dozen instructions, so the other warps hardly wait for it.  One tensor map per array and
-//     half ([N][pair_count] with the row pitch of the full matrix): columns beyond the shard's pairs and rows
-//     beyond the last step are clipped by the TMA unit, so ragged tiles and the 1..5 left-over steps need no
-//     special case;
+//     (cp.async.bulk.tensor.2d, SASS UTMASTG) per staged BOX -- [kStage rows][256 columns] of the trajectory matrix,
+//     one box per array and half for a 256-thread block, two side by side for a 512-thread one -- i.e. 2 to 8
+//     instructions per STAGE for the whole block instead of 2 (or 4) STG + address arithmetic per THREAD and step.
+//     The issuing thread's serial work between the two halves of the block barrier is a dozen instructions, so the
+//     other warps hardly wait for it.  One tensor map per array and half ([N][pair_count] with the row pitch of the
+//     full matrix): columns beyond the shard's pairs and rows beyond the last step are clipped by the TMA unit, so
+//     ragged tiles and the 1..5 left-over steps need no special case;
 //   * two stages alternate; a stage is reused only after the bulk group that read it has finished reading
 //     (cp.async.bulk.wait_group.read by the issuing thread, then the block barrier that every flush has anyway).
 // Shards whose rows cannot be cut into 16-byte aligned segments (pair count not a multiple of 16 bytes, or the lone
