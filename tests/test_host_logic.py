@@ -181,3 +181,19 @@ def test_bench_reads_roofline_traffic_from_the_committed_profile():
     traffic, source = bench.profiled_traffic()
     assert source is not None and source.startswith("profiles/") and os.path.exists(os.path.join(ROOT, source))
     assert traffic is not None and 0 <= traffic < 10_000_000             # a compute-bound kernel: kilobytes, not gigabytes
+
+
+def test_integer_widening_of_negative_floats_is_exact():
+    """csrc/heston_step.cuh widen_negative<double>: a NORMAL, strictly negative float is widened to double by
+    re-biasing the exponent with integer arithmetic (hi = (bits >> 3) + 0xA8000000, lo = bits << 29) instead of F2F.
+    The same arithmetic in NumPy must reproduce astype(float64) bit for bit, from -FLT_MIN to -FLT_MAX."""
+    rng = np.random.default_rng(5)
+    mant = rng.integers(0, 1 << 23, size=1_000_000, dtype=np.uint32)
+    expo = rng.integers(1, 255, size=mant.size, dtype=np.uint32)              # normal numbers only
+    bits = (np.uint32(1) << np.uint32(31)) | (expo << np.uint32(23)) | mant
+    bits = np.concatenate([bits, np.array([0x80800000, 0xFF7FFFFF, 0xBF800000, 0xB3800000], dtype=np.uint32)])
+    hi = ((bits >> np.uint32(3)).astype(np.uint64) + np.uint64(0xA8000000)) & np.uint64(0xFFFFFFFF)
+    lo = (bits.astype(np.uint64) << np.uint64(29)) & np.uint64(0xFFFFFFFF)
+    widened = ((hi << np.uint64(32)) | lo).view(np.float64)
+    assert np.array_equal(widened, bits.view(np.float32).astype(np.float64))
+    assert np.all(widened < 0)
