@@ -65,8 +65,9 @@ __device__ __forceinline__ void bulk_wait_reads() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Launch bounds: uncapped registers measured best -- x only: 71 registers / 3 resident blocks 0.403 ms against 0.427 ms
-// at 48 registers / 5 blocks; (x, v) is HBM-bound and within 1% for every cap tried (79 / 64 / 48 registers).
+// Launch bounds, 256-thread variants: uncapped registers measured best -- x only: 71 registers / 3 resident blocks
+// 0.403 ms against 0.427 ms at 48 registers / 5 blocks.  The 512-thread (x, v) variant is capped at 64 registers so
+// that two blocks are resident (at 256 threads it was within 1% for every cap tried: 79 / 64 / 48 registers).
 // WITH_V: also materialise the variance; BULK: TMA tensor stores from a shared-memory stage (else direct STG)
 template <typename real, bool WITH_V, bool MULTI, bool BULK>
 __global__ void __launch_bounds__((kTrajThreadsOf<real, WITH_V, BULK>),
@@ -76,7 +77,7 @@ heston_trajectory_kernel(const __grid_constant__ FusedConsts<real> c, const __gr
                          real *__restrict__ traj_x, real *__restrict__ traj_v) {
     constexpr int NARR = WITH_V ? 4 : 2;                  // staged arrays per step: x1, x2 (, v1, v2)
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    real *stage = reinterpret_cast<real *>(smem_raw);     // [2][NARR][kStage][B]: one dense box per array
+    real *stage = reinterpret_cast<real *>(smem_raw);     // [2][NARR][kSubs][kStage][kBox]: dense boxes
     constexpr int kTrajThreads = kTrajThreadsOf<real, WITH_V, BULK>;
     constexpr int kSubs = kTrajThreads / kBox;            // boxes side by side per block and array
     constexpr uint32_t B = kTrajThreads;
