@@ -92,6 +92,20 @@ class CpuArm:
         dt = time.perf_counter() - t0
         return paths * (self.nT - 1) / dt, dt, price, paths
 
+    def single_core(self, R=100_000, seed=4242):
+        """One batch on ONE worker process (the others idle): the reference's single-core rate at the bench's step
+        count (SURVEY section 8d asks for the 1-core figure beside the all-core one)."""
+        if self.kind == "reference":
+            from oracle import reference_runner as rr
+            fn, job = rr.reference_batch_price, (seed, dict(self.kwargs, R=R))
+        else:
+            fn, job = _port_batch, (seed, R, self.nT)
+        t0 = time.perf_counter()
+        self.pool.submit(fn, job).result()
+        dt = time.perf_counter() - t0
+        return {"value": R * (self.nT - 1) / dt, "unit": UNIT, "cores": 1,
+                "sample": f"{R} paths x {self.nT - 1} steps, one worker process, {dt:.2f} s"}
+
     def describe(self, paths):
         what = ("the reference's unmodified simulate_and_compute_option_price on its NumpyBundle (staged copy, "
                 "import stubs for arrayfire)" if self.kind == "reference" else "NumPy restatement of the reference path")
@@ -149,6 +163,7 @@ def run_reference(args):
     total = time.perf_counter() - t0
     value = work / total
     paths = work // (arm.nT - 1) // max(steps_run, 1)
+    single = arm.single_core()
     arm.close()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -159,7 +174,7 @@ def run_reference(args):
                                "path over all host cores, the full 10M paths per step)",
                    "paths": paths, "nT": arm.nT, "antithetic": True},
         "price": price,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "single_core": single,
                          "sample": arm.describe(paths) + f", {steps_run} steps after {warmups} warm-up steps",
                          "cpu": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -500,7 +515,8 @@ def run_b200(args):
         arm = CpuArm()
         v, dt, cpu_price, paths = arm.step(PATHS_PER_GPU, seed0=777)
         cpu = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
-               "sample": arm.describe(paths) + f", one step ({dt:.1f} s)", "cpu": cpu_model(), "price": cpu_price}
+               "sample": arm.describe(paths) + f", one step ({dt:.1f} s)", "cpu": cpu_model(), "price": cpu_price,
+               "single_core": arm.single_core()}
         arm.close()
 
     if rank == 0:
